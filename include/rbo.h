@@ -1,0 +1,181 @@
+/*
+ * rbo.h -- C ABI of librbo.so: the B200-native (sm_100a, FP64 CUDA) implementation of the Monte-Carlo
+ * rollout acquisition estimator and its adjoint gradient.
+ *
+ * The reference (DarianNwankwo/Rollout-Bayesian-Optimization) is pure Julia with no FFI; the seam this
+ * library plugs into is the Julia call
+ *     simulate_trajectory_mc(T::Trajectory, tp::TrajectoryParameters; inner_solve_xstarts, resolutions,
+ *                            spatial_gradients_container, hyperparameter_gradients_container)
+ * (rollout.jl:279-340). A Julia shim re-defines that method as marshalling + `ccall` into the entry points
+ * below (see INTEGRATION.md and rollout-bayesian-optimization_b200/julia/). Each entry point cites the
+ * reference code it replaces.
+ *
+ * Conventions: all arrays FP64, column-major (Julia layout), caller-owned, host memory unless the name
+ * says "device"; every function returns 0 (RBO_SUCCESS) or a negative error code and records a message
+ * retrievable with rbo_last_error(). A handle is bound to one CUDA device and one stream; it is
+ * thread-compatible (one thread at a time per handle). There is NO CPU fallback: without a CUDA device
+ * rbo_create() fails with RBO_ERR_CUDA.
+ */
+#ifndef RBO_H
+#define RBO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBO_ABI_VERSION 1
+
+typedef struct rbo_handle rbo_handle;
+
+enum { RBO_SUCCESS = 0, RBO_ERR_ARG = -1, RBO_ERR_CUDA = -2, RBO_ERR_STATE = -3, RBO_ERR_UNSUPPORTED = -4, RBO_ERR_NUMERIC = -5 };
+
+/* rbf.jl:60-103 : RadialBasisFunction constructors (kernel_id is derived from rbf.constructor) */
+enum { RBO_KERNEL_MATERN12 = 0, RBO_KERNEL_MATERN32 = 1, RBO_KERNEL_MATERN52 = 2, RBO_KERNEL_SE = 3, RBO_KERNEL_PERIODIC = 4 };
+/* decision_rules.jl:84-127 : DecisionRule.name */
+enum { RBO_RULE_EI = 0, RBO_RULE_POI = 1, RBO_RULE_LCB = 2 };
+/* which outputs rbo_rollout computes: resolutions only, or resolutions + gradient(T) (rollout.jl:318-323) */
+enum { RBO_MODE_VALUE = 0, RBO_MODE_VALUE_GRAD = 1 };
+/* flags */
+enum { RBO_FLAG_TEACHER_FORCED = 1 /* x_1..x_h supplied by the caller (step-level parity tests) */ };
+
+/* per-trajectory status: what the reference would have thrown for that sample */
+enum {
+  RBO_TRAJ_OK = 0,
+  RBO_TRAJ_NOT_PD_ROW = 1,      /* rbs.jl:412  PosDefException in update_cholesky! */
+  RBO_TRAJ_NEG_VARIANCE = 2,    /* rbs.jl:528  DomainError in sqrt */
+  RBO_TRAJ_NOT_PD_JOINT = 3,    /* rbs.jl:537  PosDefException in the joint value/gradient covariance */
+  RBO_TRAJ_ALL_STARTS_NAN = 4,  /* rbf_optim.jl:96-97 findmin over an empty collection */
+  RBO_TRAJ_SINGULAR_HESSIAN = 5 /* rollout.jl:188 SingularException */
+};
+
+/* per-start inner-solve status */
+enum { RBO_SOLVE_CONVERGED = 0, RBO_SOLVE_MAXIT = 1, RBO_SOLVE_STEP_TINY = 2, RBO_SOLVE_PRED_TINY = 3, RBO_SOLVE_STALLED = 4, RBO_SOLVE_NAN = 5 };
+
+/* Inner box-constrained maximiser (replaces Optim.IPNewton, rbf_optim.jl:24-30): regularised projected Newton. */
+typedef struct {
+  int32_t maxit;    /* accepted steps per start */
+  int32_t maxtry;   /* regularisation retries per step */
+  double gtol;      /* stop: max |projected gradient| <= gtol * max(1, |alpha|) */
+  double xtol;      /* stop: max |step| <= xtol * max(1, max |x|) */
+  double pred_tol;  /* stop: predicted increase <= pred_tol * max(1, |alpha|) */
+  double eta;       /* acceptance ratio */
+  double lam_min;   /* smallest non-zero shift relative to max |diag H| */
+  double lam_up, lam_down;
+} rbo_solver_opts;
+
+/* Summary of one estimator evaluation: ExpectedTrajectoryOutput (trajectory.jl:112-134) computed as
+ * rollout.jl:328-337 over the trajectories this handle processed, plus accounting for bench.py. */
+typedef struct {
+  double mean, std;             /* mu_x_theta, sigma_mu_x_theta (corrected sample std) */
+  int32_t n_traj, n_failed;     /* trajectories processed / with status != RBO_TRAJ_OK */
+  double kernel_ms;             /* device time of the rollout kernel(s), CUDA events on the handle's stream */
+  double flops;                 /* algorithmic FP64 flops (SURVEY.md 8d formula with the solver's measured evaluation counts) */
+  double flops_executed;        /* FP64 flops this implementation executes for the same work (fewer: forward-only solves) */
+  int64_t n_evals;              /* acquisition evaluations performed by the inner solves */
+  int32_t gpu_launches;         /* kernels launched by this call */
+} rbo_summary;
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+int rbo_abi_version(void);
+/* Creates a handle on CUDA device `device_id` with its own non-blocking stream. */
+int rbo_create(rbo_handle** out, int device_id);
+int rbo_destroy(rbo_handle* h);
+/* Message of the last failing call on this handle (or of rbo_create when h == NULL). */
+const char* rbo_last_error(const rbo_handle* h);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the handle's own stream. */
+int rbo_set_stream(rbo_handle* h, void* cuda_stream);
+void rbo_default_solver_opts(rbo_solver_opts* o);
+int rbo_set_solver_opts(rbo_handle* h, const rbo_solver_opts* o);
+/* htol of solve_dual_x (rollout.jl:156; the reference never overrides its default 1e-4): a policy solve whose
+ * det(H alpha) < htol contributes a zero dual (Q3). Exposed so tests can exercise the full adjoint. */
+int rbo_set_htol(rbo_handle* h, double htol);
+
+/* ---- inputs (resident on the device until replaced) ------------------------------------------ */
+/* The base surrogate the fantasy surrogate is built from: FantasySurrogate(s, h) (rbs.jl:345-381) reads
+ * fs.X[:,1:N], fs.L[1:N,1:N], fs.y[1:N], fs.cs[1], fs.sigma_n2, fs.psi, fs.g.
+ * X: d x N (ldX >= d).  L: N x N lower triangle of a column-major buffer with leading dimension ldL
+ * (Julia's LowerTriangular .data).  c = K^-1 y. */
+int rbo_set_surrogate(rbo_handle* h, int d, int N, const double* X, int ldX, const double* L, int ldL,
+                      const double* y, const double* c, double sigma_n2, int kernel_id, const double* ktheta,
+                      int nktheta, int rule_id, double sigma_tol);
+
+/* tp.rnstream_sequence (trajectory.jl:47): M_total x (d+1) x hp1, column-major, sample index fastest.
+ * This handle keeps samples [m_begin, m_begin + m_count). */
+int rbo_set_normals(rbo_handle* h, const double* rn, int M_total, int hp1, int m_begin, int m_count);
+/* gen_low_discrepancy_sequence(M_total, d, hp1) (utils.jl:65-74: Sobol -> log10 Box-Muller -> reshape)
+ * generated on the device for samples [m_begin, m_begin + m_count). Requires rbo_set_surrogate (for d). */
+int rbo_generate_normals(rbo_handle* h, int M_total, int hp1, int m_begin, int m_count);
+/* Copies the handle's normals back: out is m_count x (d+1) x hp1 column-major. */
+int rbo_get_normals(rbo_handle* h, double* out);
+/* inner_solve_xstarts (rollout.jl:282): d x S, S = number of columns (the reference passes S+2). */
+int rbo_set_starts(rbo_handle* h, const double* starts, int S);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* simulate_trajectory_mc (rollout.jl:279-340) for the handle's samples.
+ *   x0[d], lbs[d], ubs[d]   : tp.x0, tp.spatial_lbs/ubs      theta[ntheta] : tp.theta (decision-rule hypers)
+ *   horizon                 : tp.horizon (hp1 of the normals must be >= horizon + 1)
+ *   fmini                   : minimum(get_observations(base surrogate)) as the reference computes it
+ *                             (rollout.jl:109,234: over the zero-padded capacity-length vector)
+ *   dual_dirs               : d x horizon x m_count, the rand(dim) draws of solve_dual_y (rollout.jl:133),
+ *                             indexed [k, solve_index, m]; NULL = zeros. Only read in VALUE_GRAD mode.
+ *   x_forced                : d x horizon x m_count, only with RBO_FLAG_TEACHER_FORCED
+ *   values[m_count]         : resolutions (rollout.jl:318)
+ *   grad_x[d x m_count], grad_theta[ntheta x m_count] : the gradient containers (rollout.jl:321-322), may be NULL
+ *   best_index, grad_case, status : int32[m_count], may be NULL (t of rollout.jl:235; case 1/2/3 of :239-251)
+ *   summary                 : may be NULL
+ */
+int rbo_rollout(rbo_handle* h, const double* x0, const double* theta, int ntheta, const double* lbs, const double* ubs,
+                int horizon, double fmini, int mode, int flags, const double* dual_dirs, const double* x_forced,
+                double* values, double* grad_x, double* grad_theta, int32_t* best_index, int32_t* grad_case,
+                int32_t* status, rbo_summary* summary);
+
+/* Same computation, results left on the device (no per-trajectory D2H): only x0 (d doubles) goes in and the
+ * partial sums come out through rbo_get_partial_sums. Used by the SGA loop and by bench.py's device-resident
+ * timing. dual_dirs_device / x_forced_device are device pointers or NULL. */
+int rbo_rollout_device(rbo_handle* h, const double* x0, const double* theta, int ntheta, const double* lbs,
+                       const double* ubs, int horizon, double fmini, int mode, int flags,
+                       const double* dual_dirs_device, const double* x_forced_device, rbo_summary* summary);
+
+/* Per-handle partial statistics of the last rollout, for the multi-GPU all-reduce:
+ * sums = [n, n*mean_v, M2_v, n*mean_v^2, (n*mean, M2, n*mean^2) per grad_x row..., per grad_theta row...]
+ * length 1 + 3*(1 + d + ntheta). Written to a DEVICE buffer (e.g. a torch tensor handed to NCCL).
+ * M2 is the centred sum of squares around this handle's own mean (two-pass, as rollout.jl:328-337). */
+int rbo_partial_sums_device(rbo_handle* h, double* sums_device, int len);
+/* Host-side merge of all-reduced sums into means / corrected sample stds (Chan's pairwise update). */
+int rbo_finalize_sums(const double* sums, int d, int ntheta, double* mean, double* std, double* gx_mean,
+                      double* gx_std, double* gth_mean, double* gth_std);
+
+/* Tape of the last rollout (single-trajectory inspection, sample(T)/best(T) of rollout.jl:85-105, and the
+ * step-level parity tests). Any pointer may be NULL.
+ *   xs[d x (h+1) x m_count], ys[(h+1) x m_count], gys[d x (h+1) x m_count], alphas[h x m_count],
+ *   n_evals[h x m_count] (int32), start_status / start_iters [S x h x m_count] (int32) */
+int rbo_get_tape(rbo_handle* h, double* xs, double* ys, double* gys, double* alphas, int32_t* n_evals,
+                 int32_t* start_status, int32_t* start_iters);
+
+/* ---- generators the reference's host code provides (utils.jl), same arithmetic on the device -- */
+/* gen_uniform (utils.jl:4-13): dim x npoints Sobol points (Joe-Kuo, Gray code, origin skipped). */
+int rbo_sobol_uniform(rbo_handle* h, int dim, int npoints, double* out);
+int rbo_sobol_uint32(rbo_handle* h, int dim, int npoints, uint32_t* out);
+/* generate_initial_guesses (utils.jl:145-153): out is d x (S+2). */
+int rbo_generate_initial_guesses(rbo_handle* h, int S, int d, const double* lbs, const double* ubs, double* out);
+
+/* ---- myopic solve (what experiments/*_bayesopt.jl time) --------------------------------------- */
+/* multistart_base_solve!(::Surrogate, xfinal; ...) (rbf_optim.jl:103-134) against the resident base
+ * surrogate and starts: xfinal[d], and optionally the acquisition value there. */
+int rbo_multistart_base_solve(rbo_handle* h, const double* theta, int ntheta, const double* lbs, const double* ubs,
+                              double* xfinal, double* alpha, rbo_summary* summary);
+
+/* ---- measurement support ---------------------------------------------------------------------- */
+/* Dense FP64 FMA micro-benchmark on this handle's device (TFLOP/s): the roofline denominator of this path,
+ * because MEASURED_PEAKS.json carries no FP64 figure. */
+int rbo_fp64_peak(rbo_handle* h, double* tflops);
+/* Number of SMs of the handle's device. */
+int rbo_num_sms(const rbo_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBO_H */

@@ -1,0 +1,605 @@
+// rbo_api.cu -- the C ABI of librbo.so (include/rbo.h): handle, device-resident inputs, launches.
+// No CPU fallback anywhere: every entry point that computes does so with the sm_100a kernels of rollout_kernel.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rbo_kernel.cuh"
+#include "sobol_dirs.h"
+
+namespace rbo {
+__global__ void rbo_rollout_kernel(const __grid_constant__ DevProblem P);
+__global__ void rbo_normals_kernel(const unsigned* dirs, double* out, int M_total, int d, int H, int m_begin, int m_count);
+__global__ void rbo_sobol_kernel(const unsigned* dirs, unsigned* out_u32, double* out_f64, int dim, int npoints, const double* lbs, const double* ubs);
+__global__ void rbo_stats_kernel(const double* values, const double* gx, const double* gth, const int* n_evals, const int* best_index, const int* grad_case,
+                                 const int* status, int M, int d, int nth, int h, double* sums);
+__global__ void rbo_fp64_peak_kernel(double* out, int iters);
+}  // namespace rbo
+
+using namespace rbo;
+
+static thread_local std::string g_create_error;
+
+struct rbo_handle {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int num_sms = 0, max_smem = 0;
+  std::string err;
+  rbo_solver_opts so;
+  // surrogate
+  bool have_sur = false;
+  int d = 0, N = 0, N8 = 0, nb8 = 0;
+  KernelSpec kern;
+  int rule_id = 0;
+  double sigma_tol = 1e-8, sigma_n2 = 1e-6, k0 = 1, d2k0 = 0, ymin_base = 0;
+  double *Xb = nullptr, *yb = nullptr, *c0 = nullptr, *u0 = nullptr, *Lf = nullptr, *Lb = nullptr;
+  // normals / starts
+  int M = 0, hp1 = 0;
+  double* rn = nullptr;
+  int S = 0;
+  double* starts = nullptr;
+  unsigned* sobol_dirs = nullptr;
+  // outputs
+  int outM = 0, outh = -1, outS = 0, outd = 0, outnth = 0;
+  double *values = nullptr, *grad_x = nullptr, *grad_theta = nullptr, *xs = nullptr, *ys = nullptr, *gys = nullptr, *alphas = nullptr;
+  int *best_index = nullptr, *grad_case = nullptr, *status = nullptr, *n_evals = nullptr, *start_status = nullptr, *start_iters = nullptr;
+  int* work_counter = nullptr;
+  double* sums = nullptr;
+  int sums_len = 0;
+  double *dual_dirs = nullptr, *x_forced = nullptr;
+  size_t dual_cap = 0, forced_cap = 0;
+  // last call
+  int last_h = 0, last_mode = 0, last_nth = 1;
+  bool tape_enabled = true;
+  double htol = 1e-4;
+};
+
+static int fail(rbo_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(h, call)                                                                                       \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(h, RBO_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <class T>
+static cudaError_t dev_realloc(T** p, size_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (n == 0) return cudaSuccess;
+  return cudaMalloc((void**)p, n * sizeof(T));
+}
+
+extern "C" {
+
+int rbo_abi_version(void) { return RBO_ABI_VERSION; }
+
+void rbo_default_solver_opts(rbo_solver_opts* o) {
+  o->maxit = 100;
+  o->maxtry = 60;
+  o->gtol = 1e-10;
+  o->xtol = 1e-15;
+  o->pred_tol = 1e-17;
+  o->eta = 1e-4;
+  o->lam_min = 1e-8;
+  o->lam_up = 4.0;
+  o->lam_down = 0.25;
+}
+
+const char* rbo_last_error(const rbo_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rbo_create(rbo_handle** out, int device_id) {
+  if (!out) return fail(nullptr, RBO_ERR_ARG, "rbo_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, RBO_ERR_CUDA, "rbo_create: no CUDA device (%s); librbo has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device_id < 0 || device_id >= ndev) return fail(nullptr, RBO_ERR_ARG, "rbo_create: device %d out of range (have %d)", device_id, ndev);
+  rbo_handle* h = new rbo_handle();
+  h->device = device_id;
+  rbo_default_solver_opts(&h->so);
+#define CKC(call)                                                                                    \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) { fail(nullptr, RBO_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); delete h; return RBO_ERR_CUDA; } \
+  } while (0)
+  CKC(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  CKC(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major < 10) { fail(nullptr, RBO_ERR_UNSUPPORTED, "rbo_create: device sm_%d%d is not Blackwell (sm_100a required)", prop.major, prop.minor); delete h; return RBO_ERR_UNSUPPORTED; }
+  h->num_sms = prop.multiProcessorCount;
+  h->max_smem = (int)prop.sharedMemPerBlockOptin;
+  CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  CKC(cudaEventCreate(&h->ev0));
+  CKC(cudaEventCreate(&h->ev1));
+  CKC(cudaMalloc((void**)&h->work_counter, sizeof(int)));
+  CKC(cudaMalloc((void**)&h->sobol_dirs, sizeof(rbo_sobol_dirs_host)));
+  CKC(cudaMemcpy(h->sobol_dirs, rbo_sobol_dirs_host, sizeof(rbo_sobol_dirs_host), cudaMemcpyHostToDevice));
+  CKC(cudaFuncSetAttribute(rbo_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+#undef CKC
+  *out = h;
+  return RBO_SUCCESS;
+}
+
+int rbo_destroy(rbo_handle* h) {
+  if (!h) return RBO_SUCCESS;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  void* ptrs[] = {h->Xb, h->yb, h->c0, h->u0, h->Lf, h->Lb, h->rn, h->starts, h->sobol_dirs, h->values, h->grad_x, h->grad_theta, h->xs, h->ys,
+                  h->gys, h->alphas, h->best_index, h->grad_case, h->status, h->n_evals, h->start_status, h->start_iters, h->work_counter, h->sums,
+                  h->dual_dirs, h->x_forced};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return RBO_SUCCESS;
+}
+
+int rbo_set_stream(rbo_handle* h, void* cuda_stream) {
+  if (!h) return RBO_ERR_ARG;
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return RBO_SUCCESS;
+}
+
+int rbo_set_solver_opts(rbo_handle* h, const rbo_solver_opts* o) {
+  if (!h || !o) return RBO_ERR_ARG;
+  if (o->maxit < 1 || o->maxtry < 1 || !(o->lam_up > 1.0) || !(o->lam_down > 0.0 && o->lam_down < 1.0))
+    return fail(h, RBO_ERR_ARG, "rbo_set_solver_opts: invalid options");
+  h->so = *o;
+  return RBO_SUCCESS;
+}
+
+int rbo_set_htol(rbo_handle* h, double htol) {
+  if (!h) return RBO_ERR_ARG;
+  h->htol = htol;
+  return RBO_SUCCESS;
+}
+
+int rbo_set_surrogate(rbo_handle* h, int d, int N, const double* X, int ldX, const double* L, int ldL, const double* y, const double* c,
+                      double sigma_n2, int kernel_id, const double* ktheta, int nktheta, int rule_id, double sigma_tol) {
+  if (!h) return RBO_ERR_ARG;
+  if (d < 1 || d > RBO_MAXD) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_set_surrogate: d = %d outside [1, %d]", d, RBO_MAXD);
+  if (N < 1 || !X || !L || !y || !c || ldX < d || ldL < N) return fail(h, RBO_ERR_ARG, "rbo_set_surrogate: bad arguments");
+  if (kernel_id < RBO_KERNEL_MATERN12 || kernel_id > RBO_KERNEL_PERIODIC) return fail(h, RBO_ERR_ARG, "rbo_set_surrogate: unknown kernel id %d", kernel_id);
+  if (rule_id < RBO_RULE_EI || rule_id > RBO_RULE_LCB) return fail(h, RBO_ERR_ARG, "rbo_set_surrogate: unknown decision rule id %d", rule_id);
+  if (nktheta < 1 || nktheta > 4 || !ktheta) return fail(h, RBO_ERR_ARG, "rbo_set_surrogate: kernel hyper-parameters missing");
+  CK(h, cudaSetDevice(h->device));
+  const int N8 = (N + RBO_PR - 1) / RBO_PR * RBO_PR, nb8 = N8 / RBO_PR;
+  h->d = d; h->N = N; h->N8 = N8; h->nb8 = nb8;
+  h->kern.id = kernel_id;
+  for (int i = 0; i < 4; ++i) h->kern.th[i] = i < nktheta ? ktheta[i] : 0.0;
+  h->rule_id = rule_id; h->sigma_tol = sigma_tol; h->sigma_n2 = sigma_n2;
+  double a, b;
+  kern_eval(h->kern, 0.0, h->k0, a, b);
+  h->d2k0 = b;
+  // coordinate-major, padded base locations
+  std::vector<double> Xb((size_t)d * N8, 0.0), c0(N8, 0.0), u0(N8, 0.0);
+  for (int j = 0; j < N; ++j)
+    for (int p = 0; p < d; ++p) Xb[(size_t)p * N8 + j] = X[(size_t)j * ldX + p];
+  double ymin = y[0];
+  for (int j = 0; j < N; ++j) { c0[j] = c[j]; ymin = std::min(ymin, y[j]); }
+  h->ymin_base = ymin;
+  auto Lij = [&](int i, int k) -> double { return (i < N && k < N) ? L[(size_t)k * ldL + i] : (i == k ? 1.0 : 0.0); };
+  // u0 = L^-1 y (kept so that the coefficient re-solve of rbs.jl:422-429 only needs the backward half)
+  for (int i = 0; i < N; ++i) {
+    double s = y[i];
+    for (int k = 0; k < i; ++k) s -= Lij(i, k) * u0[k];
+    u0[i] = s / Lij(i, i);
+  }
+  // forward / backward panels with inverted 8x8 diagonal blocks
+  const size_t nLf = (size_t)32 * nb8 * (nb8 + 1), nLb = (size_t)8 * N8 * nb8 - (size_t)32 * nb8 * (nb8 - 1);
+  std::vector<double> Lf(nLf, 0.0), Lb(nLb, 0.0);
+  for (int ib = 0; ib < nb8; ++ib) {
+    double Dinv[8][8];
+    for (int cc = 0; cc < 8; ++cc)
+      for (int rr = 0; rr < 8; ++rr) {
+        double t = (rr == cc) ? 1.0 : 0.0;
+        for (int j = cc; j < rr; ++j) t -= Lij(8 * ib + rr, 8 * ib + j) * Dinv[j][cc];
+        Dinv[rr][cc] = (rr < cc) ? 0.0 : t / Lij(8 * ib + rr, 8 * ib + rr);
+      }
+    double* pf = Lf.data() + (size_t)32 * ib * (ib + 1);
+    const int nk = 8 * ib;
+    for (int k = 0; k < nk; ++k)
+      for (int r = 0; r < 8; ++r) pf[(size_t)k * 8 + r] = (8 * ib + r < N) ? Lij(8 * ib + r, k) : 0.0;
+    for (int kk = 0; kk < 8; ++kk)
+      for (int r = 0; r < 8; ++r) pf[(size_t)(nk + kk) * 8 + r] = Dinv[r][kk];
+    double* pb = Lb.data() + ((size_t)8 * N8 * ib - (size_t)32 * ib * (ib - 1));
+    const int k0 = 8 * (ib + 1), nkb = N8 - k0;
+    for (int kk = 0; kk < nkb; ++kk)
+      for (int r = 0; r < 8; ++r) pb[(size_t)kk * 8 + r] = (k0 + kk < N && 8 * ib + r < N) ? Lij(k0 + kk, 8 * ib + r) : 0.0;
+    for (int kk = 0; kk < 8; ++kk)
+      for (int r = 0; r < 8; ++r) pb[(size_t)(nkb + kk) * 8 + r] = Dinv[kk][r];
+  }
+  CK(h, dev_realloc(&h->Xb, Xb.size()));
+  CK(h, dev_realloc(&h->yb, (size_t)N));
+  CK(h, dev_realloc(&h->c0, (size_t)N8));
+  CK(h, dev_realloc(&h->u0, (size_t)N8));
+  CK(h, dev_realloc(&h->Lf, nLf));
+  CK(h, dev_realloc(&h->Lb, nLb));
+  CK(h, cudaMemcpyAsync(h->Xb, Xb.data(), Xb.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->yb, y, (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->c0, c0.data(), (size_t)N8 * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->u0, u0.data(), (size_t)N8 * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->Lf, Lf.data(), nLf * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->Lb, Lb.data(), nLb * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));  // the staging vectors die here
+  h->have_sur = true;
+  return RBO_SUCCESS;
+}
+
+int rbo_set_normals(rbo_handle* h, const double* rn, int M_total, int hp1, int m_begin, int m_count) {
+  if (!h) return RBO_ERR_ARG;
+  if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_set_normals: call rbo_set_surrogate first");
+  if (!rn || M_total < 1 || hp1 < 1 || m_begin < 0 || m_count < 1 || m_begin + m_count > M_total) return fail(h, RBO_ERR_ARG, "rbo_set_normals: bad arguments");
+  CK(h, cudaSetDevice(h->device));
+  const int q1 = h->d + 1;
+  CK(h, dev_realloc(&h->rn, (size_t)m_count * q1 * hp1));
+  // strided slice [m_begin, m_begin+m_count) of the sample-fastest tensor
+  CK(h, cudaMemcpy2DAsync(h->rn, (size_t)m_count * 8, rn + m_begin, (size_t)M_total * 8, (size_t)m_count * 8, (size_t)q1 * hp1, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->M = m_count; h->hp1 = hp1;
+  return RBO_SUCCESS;
+}
+
+int rbo_generate_normals(rbo_handle* h, int M_total, int hp1, int m_begin, int m_count) {
+  if (!h) return RBO_ERR_ARG;
+  if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_generate_normals: call rbo_set_surrogate first");
+  if (M_total < 1 || hp1 < 1 || m_begin < 0 || m_count < 1 || m_begin + m_count > M_total) return fail(h, RBO_ERR_ARG, "rbo_generate_normals: bad arguments");
+  const int q1 = h->d + 1, D = q1 + (q1 & 1);
+  if (D > RBO_SOBOL_MAXDIM) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_generate_normals: %d Sobol dimensions > %d", D, RBO_SOBOL_MAXDIM);
+  if ((double)M_total * hp1 >= 4294967295.0) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_generate_normals: more than 2^32 Sobol points");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, dev_realloc(&h->rn, (size_t)m_count * q1 * hp1));
+  size_t total = (size_t)m_count * q1 * hp1;
+  int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
+  rbo_normals_kernel<<<blocks, 256, 0, h->stream>>>(h->sobol_dirs, h->rn, M_total, h->d, hp1, m_begin, m_count);
+  CK(h, cudaGetLastError());
+  h->M = m_count; h->hp1 = hp1;
+  return RBO_SUCCESS;
+}
+
+int rbo_get_normals(rbo_handle* h, double* out) {
+  if (!h || !out) return RBO_ERR_ARG;
+  if (!h->rn) return fail(h, RBO_ERR_STATE, "rbo_get_normals: no normals resident");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemcpyAsync(out, h->rn, (size_t)h->M * (h->d + 1) * h->hp1 * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return RBO_SUCCESS;
+}
+
+int rbo_set_starts(rbo_handle* h, const double* starts, int S) {
+  if (!h) return RBO_ERR_ARG;
+  if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_set_starts: call rbo_set_surrogate first");
+  if (!starts || S < 1) return fail(h, RBO_ERR_ARG, "rbo_set_starts: bad arguments");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, dev_realloc(&h->starts, (size_t)S * h->d));
+  CK(h, cudaMemcpyAsync(h->starts, starts, (size_t)S * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->S = S;
+  return RBO_SUCCESS;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+static int ensure_outputs(rbo_handle* h, int M, int hor, int S, int d, int nth) {
+  if (h->outM == M && h->outh == hor && h->outS == S && h->outd == d && h->outnth == nth) return RBO_SUCCESS;
+  const int hh = std::max(hor, 1);
+  CK(h, dev_realloc(&h->values, (size_t)M));
+  CK(h, dev_realloc(&h->grad_x, (size_t)M * d));
+  CK(h, dev_realloc(&h->grad_theta, (size_t)M * nth));
+  CK(h, dev_realloc(&h->best_index, (size_t)M));
+  CK(h, dev_realloc(&h->grad_case, (size_t)M));
+  CK(h, dev_realloc(&h->status, (size_t)M));
+  CK(h, dev_realloc(&h->xs, (size_t)M * (hor + 1) * d));
+  CK(h, dev_realloc(&h->ys, (size_t)M * (hor + 1)));
+  CK(h, dev_realloc(&h->gys, (size_t)M * (hor + 1) * d));
+  CK(h, dev_realloc(&h->alphas, (size_t)M * hh));
+  CK(h, dev_realloc(&h->n_evals, (size_t)M * hh));
+  CK(h, dev_realloc(&h->start_status, (size_t)M * hh * S));
+  CK(h, dev_realloc(&h->start_iters, (size_t)M * hh * S));
+  h->sums_len = 1 + 3 * (1 + d + nth) + hh + (hor + 2) + 2;
+  CK(h, dev_realloc(&h->sums, (size_t)h->sums_len));
+  h->outM = M; h->outh = hor; h->outS = S; h->outd = d; h->outnth = nth;
+  return RBO_SUCCESS;
+}
+
+// Chooses the wave width W (starts evaluated in lock-step) so that the shared-memory plan fits.
+static bool choose_plan(const rbo_handle* h, int hor, int S, int* W_out, int* RP_out, int* NR_out, size_t* bytes_out) {
+  const int d = h->d, N8 = h->N8, CS = d + 3, NR = N8 + RBO_MAXFAN;
+  const int nadj = ncols_adjoint(d);
+  for (int nw = 1; nw <= S; ++nw) {
+    int W = (S + nw - 1) / nw;
+    int RP = std::max(W * CS, nadj);
+    if ((RP & 1) == 0) RP += 1;  // odd pitch: conflict-free column walks
+    SmemPlan pl = make_plan(d, N8, hor, W, RP, NR);
+    size_t bytes = (size_t)pl.total * 8;
+    if (bytes <= (size_t)h->max_smem) { *W_out = W; *RP_out = RP; *NR_out = NR; *bytes_out = bytes; return true; }
+    if (W == 1) break;
+  }
+  return false;
+}
+
+static double f_eval(double n, double d) { return 2 * n * n * (d + 1) + n * (4 * d * d + 11 * d + 31); }
+static double f_step(double n, double d) { return 2 * n * n * (d + 1) + 2 * n * (d + 1) * (d + 1) + 3 * n * n + (d + 1) * (d + 1) * (d + 1) / 3.0; }
+// what this implementation executes per evaluation: (d+1) forward + 1 backward substitutions, Gram + two Hessian sums
+static double f_eval_exec(double n, double d) { return n * n * (d + 2) + n * (3 * d * (d + 1) + 4 * d + 40); }
+
+static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, int ntheta, const double* lbs, const double* ubs, int horizon,
+                          double fmini, int mode, int flags, const double* dual_dirs_dev, const double* x_forced_dev, bool want_summary,
+                          rbo_summary* summary) {
+  const bool myopic = (flags & RBO_FLAG_MYOPIC_INTERNAL) != 0;
+  if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_rollout: no surrogate (rbo_set_surrogate)");
+  if (!h->rn && !myopic) return fail(h, RBO_ERR_STATE, "rbo_rollout: no normals (rbo_set_normals / rbo_generate_normals)");
+  if (!h->starts && !(flags & RBO_FLAG_TEACHER_FORCED)) return fail(h, RBO_ERR_STATE, "rbo_rollout: no starts (rbo_set_starts)");
+  if (!x0 || !theta || !lbs || !ubs || ntheta < 1) return fail(h, RBO_ERR_ARG, "rbo_rollout: bad arguments");
+  if (horizon < 0 || horizon + 1 > RBO_MAXFAN) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_rollout: horizon %d not in [0, %d]", horizon, RBO_MAXFAN - 1);
+  if (!myopic && horizon + 1 > h->hp1) return fail(h, RBO_ERR_ARG, "rbo_rollout: normals hold %d steps, horizon + 1 = %d needed", h->hp1, horizon + 1);
+  const int M = myopic ? 1 : h->M;
+  if ((flags & RBO_FLAG_TEACHER_FORCED) && !x_forced_dev) return fail(h, RBO_ERR_ARG, "rbo_rollout: teacher forcing without x_forced");
+  if (mode != RBO_MODE_VALUE && mode != RBO_MODE_VALUE_GRAD) return fail(h, RBO_ERR_ARG, "rbo_rollout: bad mode");
+  for (int a = 0; a < h->d; ++a)
+    if (!(lbs[a] <= ubs[a])) return fail(h, RBO_ERR_ARG, "rbo_rollout: lower bound above upper bound in dimension %d", a);
+  CK(h, cudaSetDevice(h->device));
+  const int S = std::max(h->S, 1);
+  int W, RP, NR;
+  size_t smem_bytes;
+  if (!choose_plan(h, horizon, S, &W, &RP, &NR, &smem_bytes))
+    return fail(h, RBO_ERR_UNSUPPORTED, "rbo_rollout: problem (d=%d, N=%d, h=%d) needs more than %d bytes of shared memory per CTA", h->d, h->N, horizon, h->max_smem);
+  int rc = ensure_outputs(h, M, horizon, S, h->d, ntheta);
+  if (rc) return rc;
+  DevProblem P;
+  memset(&P, 0, sizeof(P));
+  P.d = h->d; P.N = h->N; P.N8 = h->N8; P.nb8 = h->nb8; P.h = horizon; P.S = S; P.W = W; P.nwaves = (S + W - 1) / W;
+  P.CS = h->d + 3; P.RP = RP; P.NR = NR; P.M = M; P.hp1 = h->hp1; P.mode = mode; P.flags = flags; P.ntheta = ntheta;
+  P.kern = h->kern; P.rule_id = h->rule_id; P.sigma_tol = h->sigma_tol; P.sigma_n2 = h->sigma_n2; P.k0 = h->k0; P.d2k0 = h->d2k0;
+  P.ymin_base = h->ymin_base; P.fmini = fmini; P.theta1 = theta[0]; P.htol = h->htol; P.so = h->so;
+  for (int a = 0; a < h->d; ++a) { P.x0[a] = x0[a]; P.lbs[a] = lbs[a]; P.ubs[a] = ubs[a]; }
+  P.Xb = h->Xb; P.yb = h->yb; P.c0 = h->c0; P.u0 = h->u0; P.Lf = h->Lf; P.Lb = h->Lb; P.rn = h->rn; P.starts = h->starts;
+  P.dual_dirs = dual_dirs_dev; P.x_forced = x_forced_dev;
+  P.values = h->values; P.grad_x = h->grad_x; P.grad_theta = h->grad_theta; P.best_index = h->best_index; P.grad_case = h->grad_case;
+  P.status = h->status; P.xs = h->xs; P.ys = h->ys; P.gys = h->gys; P.alphas = h->alphas; P.n_evals = h->n_evals;
+  P.start_status = h->tape_enabled ? h->start_status : nullptr; P.start_iters = h->tape_enabled ? h->start_iters : nullptr;
+  P.work_counter = h->work_counter;
+  const int grid = std::min(M, h->num_sms);
+  CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  rbo_rollout_kernel<<<grid, RBO_THREADS, smem_bytes, h->stream>>>(P);
+  CK(h, cudaGetLastError());
+  rbo_stats_kernel<<<1, 1024, 0, h->stream>>>(h->values, mode == RBO_MODE_VALUE_GRAD ? h->grad_x : nullptr, mode == RBO_MODE_VALUE_GRAD ? h->grad_theta : nullptr,
+                                              h->n_evals, h->best_index, h->grad_case, h->status, M, h->d, ntheta, horizon, h->sums);
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->last_h = horizon; h->last_mode = mode; h->last_nth = ntheta;
+  if (want_summary && summary) {
+    std::vector<double> sums(h->sums_len);
+    CK(h, cudaMemcpyAsync(sums.data(), h->sums, (size_t)h->sums_len * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    const int d = h->d, hh = std::max(horizon, 1), nrows = 1 + d + ntheta;
+    const double n = sums[0];
+    summary->n_traj = M;
+    summary->mean = sums[1] / n;
+    summary->std = n > 1 ? std::sqrt(sums[2] / (n - 1)) : NAN;
+    summary->kernel_ms = ms;
+    summary->gpu_launches = 2;
+    const double* ev = sums.data() + 1 + 3 * nrows;
+    const double* hist = ev + hh;
+    summary->n_failed = (int)hist[horizon + 2];
+    double fl = 0, fx = 0;
+    long long ne = 0;
+    if (myopic) {
+      ne = (long long)ev[0];
+      fl = ev[0] * f_eval(h->N, d);
+      fx = ev[0] * f_eval_exec(h->N, d);
+    } else {
+      fl = M * f_step(h->N, d); fx = M * f_step(h->N, d) * 0.5;
+      for (int j = 1; j <= horizon; ++j) {
+        double nj = h->N + j, e = ev[j - 1];
+        ne += (long long)e;
+        fl += e * f_eval(nj, d) + M * f_step(nj, d);
+        fx += e * f_eval_exec(nj, d) + M * f_step(nj, d) * 0.5;
+      }
+    }
+    if (mode == RBO_MODE_VALUE_GRAD)
+      for (int t = 1; t <= horizon; ++t) {  // F_adj(t) for the hist[t] trajectories whose best step is t (case 3)
+        double fa = t * (2.0 / 3.0) * d * d * d;
+        for (int i = 1; i <= t; ++i) { double ni = h->N + i; fa += f_eval(ni, d) + i * (d + 1) * (2 * ni * ni + 6 * ni * d); }
+        fl += hist[t] * fa;
+        fx += hist[t] * fa;
+      }
+    summary->flops = fl;
+    summary->flops_executed = fx;
+    summary->n_evals = ne;
+  }
+  return RBO_SUCCESS;
+}
+
+static int upload_opt(rbo_handle* h, const double* src, size_t n, double** dst, size_t* cap) {
+  if (!src) return RBO_SUCCESS;
+  if (*cap < n) { CK(h, dev_realloc(dst, n)); *cap = n; }
+  CK(h, cudaMemcpyAsync(*dst, src, n * 8, cudaMemcpyHostToDevice, h->stream));
+  return RBO_SUCCESS;
+}
+
+extern "C" {
+
+int rbo_rollout(rbo_handle* h, const double* x0, const double* theta, int ntheta, const double* lbs, const double* ubs, int horizon, double fmini,
+                int mode, int flags, const double* dual_dirs, const double* x_forced, double* values, double* grad_x, double* grad_theta,
+                int32_t* best_index, int32_t* grad_case, int32_t* status, rbo_summary* summary) {
+  if (!h) return RBO_ERR_ARG;
+  if (!values) return fail(h, RBO_ERR_ARG, "rbo_rollout: values is NULL");
+  if (mode == RBO_MODE_VALUE_GRAD && (!grad_x || !grad_theta)) return fail(h, RBO_ERR_ARG, "rbo_rollout: gradient containers missing in VALUE_GRAD mode");
+  CK(h, cudaSetDevice(h->device));
+  const size_t nd = (size_t)h->M * std::max(horizon, 0) * h->d;
+  int rc = upload_opt(h, (mode == RBO_MODE_VALUE_GRAD) ? dual_dirs : nullptr, nd, &h->dual_dirs, &h->dual_cap);
+  if (rc) return rc;
+  rc = upload_opt(h, (flags & RBO_FLAG_TEACHER_FORCED) ? x_forced : nullptr, nd, &h->x_forced, &h->forced_cap);
+  if (rc) return rc;
+  rbo_summary local;
+  rc = launch_rollout(h, x0, theta, ntheta, lbs, ubs, horizon, fmini, mode, flags, (mode == RBO_MODE_VALUE_GRAD && dual_dirs) ? h->dual_dirs : nullptr,
+                      (flags & RBO_FLAG_TEACHER_FORCED) ? h->x_forced : nullptr, true, summary ? summary : &local);
+  if (rc) return rc;
+  const size_t M = h->M;
+  CK(h, cudaMemcpyAsync(values, h->values, M * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (mode == RBO_MODE_VALUE_GRAD) {
+    CK(h, cudaMemcpyAsync(grad_x, h->grad_x, M * h->d * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(grad_theta, h->grad_theta, M * ntheta * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (best_index) CK(h, cudaMemcpyAsync(best_index, h->best_index, M * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (grad_case) CK(h, cudaMemcpyAsync(grad_case, h->grad_case, M * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (status) CK(h, cudaMemcpyAsync(status, h->status, M * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return RBO_SUCCESS;
+}
+
+int rbo_rollout_device(rbo_handle* h, const double* x0, const double* theta, int ntheta, const double* lbs, const double* ubs, int horizon,
+                       double fmini, int mode, int flags, const double* dual_dirs_device, const double* x_forced_device, rbo_summary* summary) {
+  if (!h) return RBO_ERR_ARG;
+  return launch_rollout(h, x0, theta, ntheta, lbs, ubs, horizon, fmini, mode, flags, dual_dirs_device, x_forced_device, summary != nullptr, summary);
+}
+
+int rbo_partial_sums_device(rbo_handle* h, double* sums_device, int len) {
+  if (!h || !sums_device) return RBO_ERR_ARG;
+  const int need = 1 + 3 * (1 + h->outd + h->outnth);
+  if (!h->sums || len < need) return fail(h, RBO_ERR_ARG, "rbo_partial_sums_device: need %d doubles", need);
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemcpyAsync(sums_device, h->sums, (size_t)need * 8, cudaMemcpyDeviceToDevice, h->stream));
+  return RBO_SUCCESS;
+}
+
+int rbo_finalize_sums(const double* sums, int d, int ntheta, double* mean, double* std_, double* gx_mean, double* gx_std, double* gth_mean, double* gth_std) {
+  if (!sums) return RBO_ERR_ARG;
+  const double n = sums[0];
+  if (!(n > 0)) return RBO_ERR_ARG;
+  for (int row = 0; row < 1 + d + ntheta; ++row) {
+    const double sm = sums[1 + 3 * row], m2 = sums[2 + 3 * row], smm = sums[3 + 3 * row];
+    const double mu = sm / n;
+    // sum over groups of [M2_g + n_g (mean_g - mean)^2] = sum M2_g + sum n_g mean_g^2 - n mean^2
+    const double tot = std::max(m2 + smm - n * mu * mu, 0.0);
+    const double sd = n > 1 ? std::sqrt(tot / (n - 1)) : NAN;
+    if (row == 0) { if (mean) *mean = mu; if (std_) *std_ = sd; }
+    else if (row <= d) { if (gx_mean) gx_mean[row - 1] = mu; if (gx_std) gx_std[row - 1] = sd; }
+    else { if (gth_mean) gth_mean[row - 1 - d] = mu; if (gth_std) gth_std[row - 1 - d] = sd; }
+  }
+  return RBO_SUCCESS;
+}
+
+int rbo_get_tape(rbo_handle* h, double* xs, double* ys, double* gys, double* alphas, int32_t* n_evals, int32_t* start_status, int32_t* start_iters) {
+  if (!h) return RBO_ERR_ARG;
+  if (h->outh < 0) return fail(h, RBO_ERR_STATE, "rbo_get_tape: no rollout has run");
+  CK(h, cudaSetDevice(h->device));
+  const size_t M = h->outM, hor = h->outh, hh = std::max(h->outh, 1), d = h->outd, S = h->outS;
+  if (xs) CK(h, cudaMemcpyAsync(xs, h->xs, M * (hor + 1) * d * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (ys) CK(h, cudaMemcpyAsync(ys, h->ys, M * (hor + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (gys) CK(h, cudaMemcpyAsync(gys, h->gys, M * (hor + 1) * d * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (alphas) CK(h, cudaMemcpyAsync(alphas, h->alphas, M * hh * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (n_evals) CK(h, cudaMemcpyAsync(n_evals, h->n_evals, M * hh * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (start_status) CK(h, cudaMemcpyAsync(start_status, h->start_status, M * hh * S * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (start_iters) CK(h, cudaMemcpyAsync(start_iters, h->start_iters, M * hh * S * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return RBO_SUCCESS;
+}
+
+static int sobol_common(rbo_handle* h, int dim, int npoints, uint32_t* out_u32, double* out_f64, const double* lbs, const double* ubs) {
+  if (!h) return RBO_ERR_ARG;
+  if (dim < 1 || dim > RBO_SOBOL_MAXDIM || npoints < 1) return fail(h, RBO_ERR_ARG, "sobol: dim %d / npoints %d out of range", dim, npoints);
+  CK(h, cudaSetDevice(h->device));
+  const size_t total = (size_t)dim * npoints;
+  unsigned* du = nullptr; double* df = nullptr; double* db = nullptr;
+  if (out_u32) CK(h, cudaMalloc((void**)&du, total * 4));
+  if (out_f64) CK(h, cudaMalloc((void**)&df, total * 8));
+  if (lbs) {
+    CK(h, cudaMalloc((void**)&db, (size_t)2 * dim * 8));
+    CK(h, cudaMemcpyAsync(db, lbs, (size_t)dim * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(db + dim, ubs, (size_t)dim * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
+  rbo_sobol_kernel<<<blocks, 256, 0, h->stream>>>(h->sobol_dirs, du, df, dim, npoints, db, db ? db + dim : nullptr);
+  CK(h, cudaGetLastError());
+  if (out_u32) CK(h, cudaMemcpyAsync(out_u32, du, total * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out_f64) CK(h, cudaMemcpyAsync(out_f64, df, total * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (du) cudaFree(du);
+  if (df) cudaFree(df);
+  if (db) cudaFree(db);
+  return RBO_SUCCESS;
+}
+
+int rbo_sobol_uniform(rbo_handle* h, int dim, int npoints, double* out) { return sobol_common(h, dim, npoints, nullptr, out, nullptr, nullptr); }
+int rbo_sobol_uint32(rbo_handle* h, int dim, int npoints, uint32_t* out) { return sobol_common(h, dim, npoints, out, nullptr, nullptr, nullptr); }
+
+int rbo_generate_initial_guesses(rbo_handle* h, int S, int d, const double* lbs, const double* ubs, double* out) {
+  if (!h || !lbs || !ubs || !out || S < 0 || d < 1) return RBO_ERR_ARG;
+  if (S > 0) {
+    int rc = sobol_common(h, d, S, nullptr, out, lbs, ubs);
+    if (rc) return rc;
+  }
+  const double eps = 1e-6;  // utils.jl:146
+  for (int a = 0; a < d; ++a) { out[(size_t)S * d + a] = lbs[a] + eps; out[(size_t)(S + 1) * d + a] = ubs[a] - eps; }
+  return RBO_SUCCESS;
+}
+
+int rbo_multistart_base_solve(rbo_handle* h, const double* theta, int ntheta, const double* lbs, const double* ubs, double* xfinal, double* alpha,
+                              rbo_summary* summary) {
+  if (!h) return RBO_ERR_ARG;
+  if (!xfinal) return fail(h, RBO_ERR_ARG, "rbo_multistart_base_solve: xfinal is NULL");
+  if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_multistart_base_solve: no surrogate");
+  double x0[RBO_MAXD] = {0};
+  rbo_summary local;
+  int rc = launch_rollout(h, x0, theta, ntheta, lbs, ubs, 0, 0.0, RBO_MODE_VALUE, RBO_FLAG_MYOPIC_INTERNAL, nullptr, nullptr, true, summary ? summary : &local);
+  if (rc) return rc;
+  double a = 0;
+  int st = 0;
+  CK(h, cudaMemcpyAsync(xfinal, h->xs, (size_t)h->d * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(&a, h->values, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(&st, h->status, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (alpha) *alpha = a;
+  if (st != RBO_TRAJ_OK) return fail(h, RBO_ERR_NUMERIC, "rbo_multistart_base_solve: every start produced NaN (rbf_optim.jl:129-130 would throw)");
+  return RBO_SUCCESS;
+}
+
+int rbo_num_sms(const rbo_handle* h) { return h ? h->num_sms : 0; }
+
+int rbo_fp64_peak(rbo_handle* h, double* tflops) {
+  if (!h || !tflops) return RBO_ERR_ARG;
+  CK(h, cudaSetDevice(h->device));
+  const int blocks = h->num_sms * 4, threads = 512, iters = 4096;
+  double* out = nullptr;
+  CK(h, cudaMalloc((void**)&out, (size_t)blocks * threads * 8));
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(h, cudaEventRecord(h->ev0, h->stream));
+    rbo_fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(out, iters);
+    CK(h, cudaEventRecord(h->ev1, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    float ms;
+    CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    double fl = (double)blocks * threads * iters * 16.0 * 2.0;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaFree(out);
+  *tflops = best;
+  return RBO_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+"""Parity of the CUDA path (through the C ABI of librbo.so) with the CPU oracle on identical seeded inputs.
+
+Tolerances (FP64, stated here as north_star asks):
+  * teacher-forced step-level parity (identical x_j fed to both): 1e-9 relative on every tape entry and value;
+  * free-running parity (each side runs its own implementation of the same inner-solve algorithm): 1e-8 relative on
+    per-trajectory values, 1e-6 on gradients (relative to the largest gradient component of the trajectory), for at
+    least 99% of the trajectories -- a start sitting on a basin boundary may legitimately flip;
+  * Sobol integers: bit-exact; normals: 1e-13 relative (libm vs CUDA log10/sin/cos differ in the last ulps).
+"""
+import numpy as np
+import pytest
+
+from conftest import oracle_problem, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def setup(pkg, orc, name, **kw):
+    wl = pkg.problems.make_workload(name, **kw)
+    sur = wl.surrogate()
+    rn = orc.gen_low_discrepancy_sequence(wl.M, wl.d, wl.h + 1)
+    starts = orc.generate_initial_guesses(wl.S, wl.lbs, wl.ubs)
+    dd = np.asfortranarray(np.random.default_rng(7).random((wl.d, max(wl.h, 1), wl.M)))
+    return wl, sur, rn, starts, dd
+
+
+def gpu_rollout(pkg, wl, sur, rn, starts, dd=None, x_forced=None, grad=True, htol=None, tape=True):
+    eng = pkg.RolloutEngine(0)
+    try:
+        if htol is not None:
+            eng.set_htol(htol)
+        eng.set_surrogate(pkg.FantasySurrogate(sur, wl.h))
+        eng.set_normals(rn)
+        eng.set_starts(starts)
+        M = wl.M
+        out = dict(values=np.zeros(M), grad_x=np.zeros((wl.d, M), order="F"), grad_theta=np.zeros((1, M), order="F"),
+                   best_index=np.zeros(M, np.int32), grad_case=np.zeros(M, np.int32), status=np.zeros(M, np.int32))
+        s = eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), out["values"],
+                        out["grad_x"] if grad else None, out["grad_theta"] if grad else None, dual_dirs=dd if grad else None,
+                        x_forced=x_forced, best_index=out["best_index"], grad_case=out["grad_case"], status=out["status"])
+        out["summary"] = s
+        if tape:
+            out.update(eng.tape(wl.h))
+        return out
+    finally:
+        eng.close()
+
+
+def frac_within(a, b, tol, floor):
+    err = np.abs(a - b) / np.maximum(floor, np.abs(b))
+    return float(np.mean(err <= tol)), float(err.max())
+
+
+@pytest.mark.parametrize("name,kw", [("C1", dict(M=64)), ("C2", dict(M=96, S=10)), ("GP:2:0.25", dict(M=64, N=12, h=3)),
+                                     ("GP:3:0.4", dict(M=48, N=37, h=7, S=3))])
+def test_teacher_forced_step_parity(pkg, orc, name, kw):
+    wl, sur, rn, starts, dd = setup(pkg, orc, name, **kw)
+    ref = oracle_problem(orc, wl, sur, rn, starts, 1, dual_dirs=dd).rollout()
+    xf = np.asfortranarray(ref["xs"][:, 1:, :])
+    got = gpu_rollout(pkg, wl, sur, rn, starts, dd, x_forced=xf)
+    assert np.array_equal(got["status"], ref["status"])
+    assert relerr(got["ys"], ref["ys"]) < 1e-9
+    assert relerr(got["gys"], ref["gys"]) < 1e-8
+    assert relerr(got["values"], ref["values"]) < 1e-9
+    assert np.array_equal(got["best_index"], ref["best_index"]) and np.array_equal(got["grad_case"], ref["grad_case"])
+    gscale = np.maximum(np.abs(ref["grad_x"]).max(axis=0, keepdims=True), 1e-6)
+    assert np.max(np.abs(got["grad_x"] - ref["grad_x"]) / gscale) < 1e-6
+    tscale = np.maximum(np.abs(ref["grad_theta"]), 1e-6)
+    assert np.max(np.abs(got["grad_theta"] - ref["grad_theta"]) / tscale) < 1e-6
+
+
+def test_teacher_forced_full_adjoint_htol_off(pkg, orc):
+    """htol = -inf keeps every case-3 dual alive (rollout.jl:159 never fires), exercising all perturbation pushes."""
+    wl, sur, rn, starts, dd = setup(pkg, orc, "GP:3:0.4", M=64, N=20, h=4, S=3)
+    P = oracle_problem(orc, wl, sur, rn, starts, 1, dual_dirs=dd)
+    P.p.htol = -np.inf
+    ref = P.rollout()
+    assert (ref["grad_case"] == 3).sum() > 10
+    got = gpu_rollout(pkg, wl, sur, rn, starts, dd, x_forced=np.asfortranarray(ref["xs"][:, 1:, :]), htol=-np.inf)
+    gscale = np.maximum(np.abs(ref["grad_x"]).max(axis=0, keepdims=True), 1e-6)
+    assert np.max(np.abs(got["grad_x"] - ref["grad_x"]) / gscale) < 1e-6
+    assert np.max(np.abs(got["grad_theta"] - ref["grad_theta"]) / np.maximum(np.abs(ref["grad_theta"]), 1e-6)) < 1e-6
+
+
+@pytest.mark.parametrize("name,kw", [("C1", dict()), ("C2", dict(M=128)), ("GP:2:0.25", dict(M=128, N=12, h=3)),
+                                     ("C4", dict(M=32, S=20)), ("C3", dict(M=24, N=64, h=2))])
+def test_free_running_parity(pkg, orc, name, kw):
+    wl, sur, rn, starts, dd = setup(pkg, orc, name, **kw)
+    ref = oracle_problem(orc, wl, sur, rn, starts, 1, dual_dirs=dd).rollout()
+    got = gpu_rollout(pkg, wl, sur, rn, starts, dd)
+    assert np.array_equal(got["status"], ref["status"])
+    fv, ev = frac_within(got["values"], ref["values"], 1e-8, 1.0)
+    fx, ex = frac_within(got["xs"], ref["xs"], 1e-7, 1.0)
+    gscale = np.maximum(np.abs(ref["grad_x"]).max(axis=0, keepdims=True), 1e-6)
+    gerr = np.max(np.abs(got["grad_x"] - ref["grad_x"]) / gscale, axis=0)
+    fg = float(np.mean(gerr <= 1e-6))
+    print(f"{name}: values within 1e-8: {fv:.4f} (max {ev:.2e}); x-path within 1e-7: {fx:.4f} (max {ex:.2e}); grads within 1e-6: {fg:.4f}")
+    assert fv >= 0.99 and fg >= 0.98
+    assert abs(got["summary"].mean - ref["values"].mean()) <= 1e-8 * max(1, abs(ref["values"].mean())) + 0.02 * ref["values"].std()
+
+
+def test_value_only_mode_and_summary(pkg, orc):
+    wl, sur, rn, starts, dd = setup(pkg, orc, "C2", M=64, S=8)
+    ref = oracle_problem(orc, wl, sur, rn, starts, 0).rollout()
+    got = gpu_rollout(pkg, wl, sur, rn, starts, grad=False)
+    fv, ev = frac_within(got["values"], ref["values"], 1e-8, 1.0)
+    assert fv >= 0.99
+    s = got["summary"]
+    assert s.n_traj == 64 and s.n_failed == 0 and s.gpu_launches >= 1 and s.flops > 0 and s.kernel_ms > 0
+    assert np.isclose(s.mean, got["values"].mean(), rtol=1e-12) and np.isclose(s.std, got["values"].std(ddof=1), rtol=1e-10)
+    assert np.array_equal(got["n_evals"] > 0, np.ones_like(got["n_evals"], dtype=bool))
+
+
+def test_multi_wave_equals_oracle(pkg, orc):
+    """More starts than fit one wave: waves must preserve 'first minimum wins' across the whole start list."""
+    wl, sur, rn, starts, dd = setup(pkg, orc, "C4", M=16, S=126, h=1)
+    ref = oracle_problem(orc, wl, sur, rn, starts, 0).rollout()
+    got = gpu_rollout(pkg, wl, sur, rn, starts, grad=False)
+    fx, ex = frac_within(got["xs"], ref["xs"], 1e-7, 1.0)
+    assert fx == 1.0, ex
+
+
+def test_device_sobol_and_normals(pkg, orc):
+    eng = pkg.RolloutEngine(0)
+    try:
+        u = np.zeros((22, 1000), dtype=np.uint32, order="F")
+        import ctypes as C
+        eng.handle.check(eng.lib.rbo_sobol_uint32(eng.handle.h, 22, 1000, u.ctypes.data_as(C.POINTER(C.c_uint32))))
+        assert np.array_equal(u, orc.sobol_uint32(22, 1000))  # bit-exact
+    finally:
+        eng.close()
+    for (M, d, H) in ((64, 2, 2), (100, 6, 4), (33, 10, 6)):
+        got = pkg.gen_low_discrepancy_sequence(M, d, H)
+        ref = orc.gen_low_discrepancy_sequence(M, d, H)
+        assert np.allclose(got, ref, rtol=1e-13, atol=1e-15)
+    assert np.array_equal(pkg.gen_uniform(50, dim=5), orc.sobol_uniform(5, 50))
+    lbs, ubs = np.array([-5.0, 0.0, 1.0]), np.array([10.0, 15.0, 2.0])
+    assert np.allclose(pkg.generate_initial_guesses(16, lbs, ubs), orc.generate_initial_guesses(16, lbs, ubs), rtol=1e-15)
+
+
+def test_sharded_normals_equal_full(pkg, orc):
+    """A handle that owns samples [m0, m0+mc) generates / receives exactly that slice (multi-GPU sharding)."""
+    wl, sur, rn, starts, dd = setup(pkg, orc, "C2", M=40, S=4)
+    eng = pkg.RolloutEngine(0)
+    try:
+        eng.set_surrogate(pkg.FantasySurrogate(sur, wl.h))
+        eng.generate_normals(wl.M, wl.h + 1, 10, 17)
+        a = eng.get_normals(wl.h + 1)
+        eng.set_normals(rn, 10, 17)
+        b = eng.get_normals(wl.h + 1)
+    finally:
+        eng.close()
+    assert np.allclose(a, rn[10:27], rtol=1e-13, atol=1e-15) and np.array_equal(b, rn[10:27])
+
+
+def test_myopic_multistart_base_solve(pkg, orc):
+    wl, sur, rn, starts, dd = setup(pkg, orc, "C2", M=1, S=16)
+    ref = oracle_problem(orc, wl, sur, rn, starts, 0).multistart()
+    x = np.zeros(wl.d)
+    alpha, s = pkg.multistart_base_solve(sur, x, spatial_lbs=wl.lbs, spatial_ubs=wl.ubs, guesses=starts, θfixed=wl.theta)
+    assert relerr(x, ref["x"]) < 1e-7 and np.isclose(alpha, -ref["f"], rtol=1e-8)
+
+
+def test_api_errors_are_loud(pkg):
+    eng = pkg.RolloutEngine(0)
+    try:
+        with pytest.raises(pkg.RboError):
+            eng.handle.check(eng.lib.rbo_generate_normals(eng.handle.h, 8, 2, 0, 8))  # no surrogate yet
+        wl = pkg.problems.make_workload("C1")
+        eng.set_surrogate(wl.surrogate())
+        eng.generate_normals(8, 2)
+        with pytest.raises(pkg.RboError):  # no starts
+            eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, 1, 0.0, np.zeros(8))
+        eng.set_starts(np.asfortranarray(np.random.rand(2, 3)))
+        with pytest.raises(pkg.RboError):  # horizon beyond the normals
+            eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, 3, 0.0, np.zeros(8))
+        with pytest.raises(pkg.RboError):  # horizon beyond RBO_MAXFAN
+            eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, 9, 0.0, np.zeros(8))
+    finally:
+        eng.close()

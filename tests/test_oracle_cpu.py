@@ -1,0 +1,202 @@
+"""CPU tests that pin the oracle (oracle/rbo_oracle.cpp) as far as it can be pinned without Julia:
+closed forms and finite differences (the reference's own test idiom, runtests.jl:11-20), scipy's Sobol,
+and an independent numpy restatement (oracle/py_restatement.py)."""
+import numpy as np
+import pytest
+from scipy.stats import qmc
+
+from conftest import oracle_problem, relerr
+from oracle import py_restatement as pr
+
+
+def small_problem(pkg, orc, name="C2", M=6, N=14, h=2, S=4, mode=1, seed=3, **kw):
+    wl = pkg.problems.make_workload(name, M=M, N=N, h=h, S=S, seed=seed)
+    sur = wl.surrogate()
+    rn = orc.gen_low_discrepancy_sequence(M, wl.d, h + 1)
+    starts = orc.generate_initial_guesses(S, wl.lbs, wl.ubs)
+    dd = np.asfortranarray(np.random.default_rng(seed).random((wl.d, max(h, 1), M)))
+    return wl, sur, rn, starts, dd, oracle_problem(orc, wl, sur, rn, starts, mode, dual_dirs=dd, **kw)
+
+
+@pytest.mark.parametrize("kernel,theta", [("matern52", (0.456,)), ("matern32", (0.456,)), ("matern12", (0.456,)), ("se", (0.456,)), ("periodic", (0.8, 1.3))])
+def test_kernel_derivatives_fd(orc, kernel, theta):
+    # runtests.jl:23-54: rho = 0.123, theta = 0.456, h = 1e-6, rtol 1e-8 (second derivative via the first)
+    rho, h = 0.123, 1e-6
+    p, dp, d2p = orc.kernel_scalars(kernel, theta, rho)
+    fp = (orc.kernel_scalars(kernel, theta, rho + h)[0] - orc.kernel_scalars(kernel, theta, rho - h)[0]) / (2 * h)
+    fdp = (orc.kernel_scalars(kernel, theta, rho + h)[1] - orc.kernel_scalars(kernel, theta, rho - h)[1]) / (2 * h)
+    assert abs(fp - dp) <= 1e-8 * max(1, abs(dp))
+    assert abs(fdp - d2p) <= 1e-7 * max(1, abs(d2p))
+
+
+def test_matern52_closed_forms(orc):
+    # psi' = -(5 rho / 3 l^2)(1+s) e^-s, psi'' = (5 / 3 l^2)(s^2 - s - 1) e^-s
+    for rho in (0.0, 1e-3, 0.3, 2.0):
+        l = 0.7
+        s = np.sqrt(5) * rho / l
+        p, dp, d2p = orc.kernel_scalars("matern52", (l,), rho)
+        assert np.isclose(p, (1 + s + s * s / 3) * np.exp(-s), rtol=1e-14)
+        assert np.isclose(dp, -(5 * rho / (3 * l * l)) * (1 + s) * np.exp(-s), rtol=1e-13, atol=1e-300)
+        assert np.isclose(d2p, (5 / (3 * l * l)) * (s * s - s - 1) * np.exp(-s), rtol=1e-13)
+        assert np.isclose(p, pr.psi52(rho, l), rtol=1e-14) and np.isclose(d2p, pr.d2psi52(rho, l), rtol=1e-13)
+
+
+def test_surrogate_eval_fd_ladder(pkg, orc):
+    # runtests.jl:83-118: mu, sigma, alpha and their gradient / Hessian against centred differences
+    wl, sur, rn, starts, dd, P = small_problem(pkg, orc, N=20)
+    rng = np.random.default_rng(0)
+    Xf = np.asfortranarray(rng.random((wl.d, 2)))
+    yf = np.array([-0.3, 0.1])
+    x = rng.random(wl.d)
+    e = P.eval_point(x, Xf, yf)
+    hstep = 1e-5
+    for key, gkey, Hkey in (("mu", "dmu", "Hmu"), ("sigma", "dsigma", "Hsigma"), ("alpha", "dalpha", "Halpha_true")):
+        g_fd = np.zeros(wl.d)
+        H_fd = np.zeros((wl.d, wl.d))
+        for a in range(wl.d):
+            dx = np.zeros(wl.d); dx[a] = hstep
+            ep, em = P.eval_point(x + dx, Xf, yf), P.eval_point(x - dx, Xf, yf)
+            g_fd[a] = (ep[key] - em[key]) / (2 * hstep)
+            H_fd[:, a] = (ep[gkey] - em[gkey]) / (2 * hstep)
+        assert relerr(e[gkey], g_fd, floor=np.abs(g_fd).max()) < 1e-7, key
+        assert relerr(e[Hkey], H_fd, floor=np.abs(H_fd).max()) < 1e-6, key
+    # Q1: the reference's H alpha omits the mu-sigma cross term and therefore does NOT match finite differences
+    assert relerr(e["Halpha_ref"], H_fd, floor=np.abs(H_fd).max()) > 1e-3
+
+
+def test_ei_partials_fd(pkg, orc):
+    # decision_rules.jl:23-34 partials against differences of g in (mu, sigma, theta)
+    from scipy.special import erfc
+    def g(mu, s, th, fs):
+        z = (fs - mu - th) / s
+        return (fs - mu - th) * 0.5 * erfc(-z / np.sqrt(2)) + s * np.exp(-0.5 * z * z) / np.sqrt(2 * np.pi)
+    mu, s, th, fs, h = 0.3, 0.7, 0.05, 0.1, 1e-5
+    e = pr.ei_partials(mu, s, th, fs)
+    assert np.isclose(e["g"], g(mu, s, th, fs), rtol=1e-14)
+    assert np.isclose(e["g_mu"], (g(mu + h, s, th, fs) - g(mu - h, s, th, fs)) / (2 * h), rtol=1e-8)
+    assert np.isclose(e["g_sig"], (g(mu, s + h, th, fs) - g(mu, s - h, th, fs)) / (2 * h), rtol=1e-8)
+    assert np.isclose(e["g_mumu"], (g(mu + h, s, th, fs) - 2 * g(mu, s, th, fs) + g(mu - h, s, th, fs)) / h**2, rtol=1e-5)
+    assert np.isclose(e["g_sigsig"], (g(mu, s + h, th, fs) - 2 * g(mu, s, th, fs) + g(mu, s - h, th, fs)) / h**2, rtol=1e-5)
+
+
+def test_sobol_matches_scipy_joe_kuo(orc):
+    for dim in (1, 2, 3, 7, 12, 22):
+        n = 300
+        ref = qmc.Sobol(dim, scramble=False).random_base2(9)[1:n + 1]  # scipy's first point is the origin
+        got = orc.sobol_uniform(dim, n)
+        assert np.array_equal(got.T, ref)
+    # Sobol.jl's documented 2-D prefix
+    assert np.array_equal(orc.sobol_uniform(2, 5).T, np.array([[.5, .5], [.75, .25], [.25, .75], [.375, .375], [.875, .875]]))
+
+
+def test_low_discrepancy_sequence_known_answer(orc):
+    # SURVEY.md Appendix C (derived, not reference truth): gen_low_discrepancy_sequence(4, 2, 2)
+    R = orc.gen_low_discrepancy_sequence(4, 2, 2)
+    assert R.shape == (4, 3, 2)
+    assert np.allclose(R[0], [[-0.77592524854393186, 0.24081517181790421], [3.06e-17, 0.45179639513383107], [-2.02e-16, -0.95031046873742475]], rtol=1e-12, atol=1e-15)
+    assert np.isclose(R[1, 1, 0], 0.49987745820010715, rtol=1e-13) and np.isclose(R[1, 2, 0], -1.0973240098785431, rtol=1e-13)
+    # independent emulation of utils.jl:23-43, 65-74 with scipy
+    M, d, H = 5, 3, 3
+    D = d + 1
+    S = qmc.Sobol(D, scramble=False).random_base2(5)[1:M * H + 1].T
+    Nn = np.zeros_like(S)
+    for i in range(D):
+        if i % 2 == 0:
+            Nn[i] = np.sqrt(-2 * np.log10(S[i])) * np.cos(2 * np.pi * S[i + 1])
+        else:
+            Nn[i] = np.sqrt(-2 * np.log10(S[i - 1])) * np.sin(2 * np.pi * S[i])
+    ref = Nn.reshape(-1, order="F").reshape((M, D, H), order="F")
+    assert np.allclose(orc.gen_low_discrepancy_sequence(M, d, H), ref, rtol=1e-13, atol=1e-16)
+
+
+def test_initial_guesses(orc):
+    lbs, ubs = np.array([-5.0, 0.0]), np.array([10.0, 15.0])
+    G = orc.generate_initial_guesses(3, lbs, ubs)
+    assert G.shape == (2, 5)
+    assert np.allclose(G[:, 0], lbs + 0.5 * (ubs - lbs))
+    assert np.allclose(G[:, 3], lbs + 1e-6) and np.allclose(G[:, 4], ubs - 1e-6)
+
+
+def test_fit_surrogate_matches_scipy(pkg, orc):
+    wl = pkg.problems.make_workload("C2", N=30)
+    K, L, c = orc.fit_surrogate(wl.X, wl.y, "matern52", (wl.ell,), 1e-6)
+    sur = wl.surrogate()
+    assert relerr(K, sur.K[:30, :30]) < 1e-14 and relerr(L, sur.L[:30, :30]) < 1e-12 and relerr(c, sur.c[:30]) < 1e-9
+
+
+def test_oracle_vs_numpy_restatement_teacher_forced(pkg, orc):
+    """Forward draws, conditioning and the three-case adjoint gradient of the C++ oracle against the independent
+    numpy transcription, on the x-path the oracle's own inner solve produced."""
+    wl, sur, rn, starts, dd, P = small_problem(pkg, orc, M=8, N=12, h=3, S=4)
+    r = P.rollout()
+    assert np.all(r["status"] == 0)
+    cases = set()
+    for m in range(wl.M):
+        z = rn[m, :, :]
+        fs, obs, grads = pr.rollout_teacher_forced(wl.X, wl.y, wl.ell, wl.sigma_n2, wl.h, wl.x0, wl.theta, z, r["xs"][:, 1:, m])
+        assert relerr(obs, r["ys"][:, m]) < 1e-9
+        assert relerr(grads, r["gys"][:, :, m]) < 1e-8
+        gx, gth, case, t = pr.trajectory_gradient(fs, obs, grads, wl.theta, float(np.min(sur.y)), dd[:, :, m])
+        assert case == r["grad_case"][m] and t == r["best_index"][m]
+        cases.add(case)
+        assert relerr(gx, r["grad_x"][:, m], floor=max(1e-6, np.abs(gx).max())) < 1e-6, (m, case, gx, r["grad_x"][:, m])
+        assert relerr(gth, r["grad_theta"][:, m], floor=max(1e-6, np.abs(gth).max())) < 1e-6
+        assert np.isclose(r["values"][m], max(float(np.min(sur.y)) - obs.min(), 0.0), rtol=1e-10, atol=1e-12)
+    assert 3 in cases
+
+
+def test_case3_gradients_are_exercised(pkg, orc):
+    """With htol = 1e-4 (rollout.jl:156) and an even dimension some case-3 duals survive the det test (Q3)."""
+    wl, sur, rn, starts, dd, P = small_problem(pkg, orc, name="GP:2:0.25", M=64, N=12, h=3, S=4)
+    r = P.rollout()
+    c3 = r["grad_case"] == 3
+    assert c3.sum() > 0
+    nz = np.abs(r["grad_x"][:, c3]).max(axis=0) > 0
+    assert nz.sum() > 0
+    # and the numpy restatement agrees on those trajectories
+    for m in np.nonzero(c3)[0][nz][:6]:
+        fs, obs, grads = pr.rollout_teacher_forced(wl.X, wl.y, wl.ell, wl.sigma_n2, wl.h, wl.x0, wl.theta, rn[m], r["xs"][:, 1:, m])
+        gx, gth, case, t = pr.trajectory_gradient(fs, obs, grads, wl.theta, float(np.min(sur.y)), dd[:, :, m])
+        assert case == 3 and relerr(gx, r["grad_x"][:, m], floor=np.abs(gx).max()) < 1e-6
+        assert relerr(gth, r["grad_theta"][:, m], floor=max(np.abs(gth).max(), 1e-9)) < 1e-6
+
+
+def test_fast_perturbation_equals_dense(pkg, orc):
+    wl, sur, rn, starts, dd, P = small_problem(pkg, orc, name="GP:2:0.25", M=32, N=12, h=3, S=4)
+    r = P.rollout(tape=False)
+    wl2, sur2, rn2, st2, dd2, P2 = small_problem(pkg, orc, name="GP:2:0.25", M=32, N=12, h=3, S=4, flags=orc.FLAG_FAST_PERTURB)
+    r2 = P2.rollout(tape=False)
+    assert relerr(r2["grad_x"], r["grad_x"], floor=1e-3) < 1e-9
+    assert relerr(r2["values"], r["values"]) < 1e-12
+
+
+def test_factored_formulation_close(pkg, orc):
+    """sigma^2 = k0 - |L^-1 kx|^2 (what the CUDA path evaluates) against the reference's k0 - kx.(K^-1 kx)."""
+    wl, sur, rn, starts, dd, P = small_problem(pkg, orc, M=4, N=30, h=1, S=3)
+    wl2, sur2, rn2, st2, dd2, P2 = small_problem(pkg, orc, M=4, N=30, h=1, S=3, flags=orc.FLAG_FACTORED)
+    x = np.random.default_rng(5).random(wl.d)
+    e1, e2 = P.eval_point(x), P2.eval_point(x)
+    for k in ("mu", "sigma", "alpha"):
+        assert np.isclose(e1[k], e2[k], rtol=1e-10)
+    assert relerr(e1["Halpha_true"], e2["Halpha_true"], floor=np.abs(e1["Halpha_true"]).max()) < 1e-9
+
+
+def test_inner_solve_converges_and_is_deterministic(pkg, orc):
+    wl, sur, rn, starts, dd, P = small_problem(pkg, orc, M=1, N=20, h=1, S=6)
+    a, b = P.multistart(), P.multistart()
+    assert np.array_equal(a["x"], b["x"]) and a["f"] == b["f"]
+    assert a["rc"] == 0 and np.all(a["x"] >= wl.lbs) and np.all(a["x"] <= wl.ubs)
+    # at the reported maximiser the projected gradient is tiny
+    e = P.eval_point(a["x"])
+    g = -e["dalpha"]
+    free = ~(((a["x"] <= wl.lbs) & (g > 0)) | ((a["x"] >= wl.ubs) & (g < 0)))
+    assert np.abs(g[free]).max(initial=0.0) < 1e-7
+    # first minimum wins (rbf_optim.jl:97)
+    k = int(np.nanargmin(a["start_f"]))
+    assert np.allclose(a["x"], a["start_x"][:, k])
+
+
+def test_mean_std_matches_numpy(orc):
+    v = np.random.default_rng(1).random(1000)
+    m, s = orc.mean_std(v)
+    assert np.isclose(m, v.mean(), rtol=1e-14) and np.isclose(s, v.std(ddof=1), rtol=1e-12)
