@@ -321,18 +321,21 @@ static int ensure_outputs(rbo_handle* h, int M, int hor, int S, int d, int nth) 
   return RBO_SUCCESS;
 }
 
-// Chooses the wave width W (starts evaluated in lock-step) so that the shared-memory plan fits.
-static bool choose_plan(const rbo_handle* h, int hor, int S, int* W_out, int* RP_out, int* NR_out, size_t* bytes_out) {
+// Chooses the number of start slots W (starts evaluated in lock-step) so that the shared-memory plan fits.
+struct PlanChoice { int W, RP, NR, RSmax, NPmax; size_t bytes; };
+static bool choose_plan(const rbo_handle* h, int hor, int S, PlanChoice* pc) {
   const int d = h->d, N8 = h->N8, CS = d + 3, NR = N8 + RBO_MAXFAN;
   const int nadj = ncols_adjoint(d);
-  for (int nw = 1; nw <= S; ++nw) {
-    int W = (S + nw - 1) / nw;
-    int RP = std::max(W * CS, nadj);
+  for (int W = std::min(S, RBO_NWARPS); W >= 1; --W) {
+    // prefer a W that divides the start list into equal passes (fewer idle slots at the tail)
+    int RP = std::max(W * CS, nadj) + 2;
     if ((RP & 1) == 0) RP += 1;  // odd pitch: conflict-free column walks
-    SmemPlan pl = make_plan(d, N8, hor, W, RP, NR);
-    size_t bytes = (size_t)pl.total * 8;
-    if (bytes <= (size_t)h->max_smem) { *W_out = W; *RP_out = RP; *NR_out = NR; *bytes_out = bytes; return true; }
-    if (W == 1) break;
+    for (int RSmax = 4; RSmax >= 1; RSmax >>= 1) {
+      int NPmax = npairs_max(d, W);
+      SmemPlan pl = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax);
+      size_t bytes = (size_t)pl.total * 8;
+      if (bytes <= (size_t)h->max_smem) { *pc = {W, RP, NR, RSmax, NPmax, bytes}; return true; }
+    }
   }
   return false;
 }
@@ -359,16 +362,15 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
     if (!(lbs[a] <= ubs[a])) return fail(h, RBO_ERR_ARG, "rbo_rollout: lower bound above upper bound in dimension %d", a);
   CK(h, cudaSetDevice(h->device));
   const int S = std::max(h->S, 1);
-  int W, RP, NR;
-  size_t smem_bytes;
-  if (!choose_plan(h, horizon, S, &W, &RP, &NR, &smem_bytes))
+  PlanChoice pc;
+  if (!choose_plan(h, horizon, S, &pc))
     return fail(h, RBO_ERR_UNSUPPORTED, "rbo_rollout: problem (d=%d, N=%d, h=%d) needs more than %d bytes of shared memory per CTA", h->d, h->N, horizon, h->max_smem);
   int rc = ensure_outputs(h, M, horizon, S, h->d, ntheta);
   if (rc) return rc;
   DevProblem P;
   memset(&P, 0, sizeof(P));
-  P.d = h->d; P.N = h->N; P.N8 = h->N8; P.nb8 = h->nb8; P.h = horizon; P.S = S; P.W = W; P.nwaves = (S + W - 1) / W;
-  P.CS = h->d + 3; P.RP = RP; P.NR = NR; P.M = M; P.hp1 = h->hp1; P.mode = mode; P.flags = flags; P.ntheta = ntheta;
+  P.d = h->d; P.N = h->N; P.N8 = h->N8; P.nb8 = h->nb8; P.h = horizon; P.S = S; P.W = pc.W; P.RSmax = pc.RSmax; P.NPmax = pc.NPmax;
+  P.CS = h->d + 3; P.RP = pc.RP; P.NR = pc.NR; P.M = M; P.hp1 = h->hp1; P.mode = mode; P.flags = flags; P.ntheta = ntheta;
   P.kern = h->kern; P.rule_id = h->rule_id; P.sigma_tol = h->sigma_tol; P.sigma_n2 = h->sigma_n2; P.k0 = h->k0; P.d2k0 = h->d2k0;
   P.ymin_base = h->ymin_base; P.fmini = fmini; P.theta1 = theta[0]; P.htol = h->htol; P.so = h->so;
   for (int a = 0; a < h->d; ++a) { P.x0[a] = x0[a]; P.lbs[a] = lbs[a]; P.ubs[a] = ubs[a]; }
@@ -381,7 +383,7 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   const int grid = std::min(M, h->num_sms);
   CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
   CK(h, cudaEventRecord(h->ev0, h->stream));
-  rbo_rollout_kernel<<<grid, RBO_THREADS, smem_bytes, h->stream>>>(P);
+  rbo_rollout_kernel<<<grid, RBO_THREADS, pc.bytes, h->stream>>>(P);
   CK(h, cudaGetLastError());
   rbo_stats_kernel<<<1, 1024, 0, h->stream>>>(h->values, mode == RBO_MODE_VALUE_GRAD ? h->grad_x : nullptr, mode == RBO_MODE_VALUE_GRAD ? h->grad_theta : nullptr,
                                               h->n_evals, h->best_index, h->grad_case, h->status, M, h->d, ntheta, horizon, h->sums);

@@ -8,7 +8,8 @@
 #include "../../include/rbo.h"
 
 #define RBO_MAXD 32      // max input dimension d
-#define RBO_THREADS 256  // threads per CTA of the rollout kernel
+#define RBO_THREADS 512  // threads per CTA of the rollout kernel
+#define RBO_NWARPS (RBO_THREADS / 32)
 #define RBO_PR 8         // rows per factor panel
 #define RBO_MAXFAN 8     // fantasy rows per trajectory (h + 1 <= 8)
 #define RBO_FLAG_MYOPIC_INTERNAL (1 << 16)  // kernel-internal: myopic multistart against the base surrogate

@@ -8,8 +8,9 @@ namespace rbo {
 struct DevProblem {
   // sizes
   int d, N, N8, nb8;      // input dim; base observations; N rounded up to RBO_PR; N8 / RBO_PR
-  int h, S, W, nwaves;    // horizon; start columns; starts processed together (wave); ceil(S / W)
+  int h, S, W;            // horizon; start columns; start slots evaluated together in one lock-step round
   int CS, RP, NR;         // columns per start slot (d+3); padded V row pitch (doubles); V rows (N8 + RBO_MAXFAN)
+  int RSmax, NPmax;       // row splits of the reductions; capacity of the pair list
   int M;                  // trajectories owned by this handle
   int hp1;                // third dimension of the normals tensor
   int mode, flags, ntheta;
@@ -51,20 +52,26 @@ struct DevProblem {
 // Shared-memory plan (offsets in doubles from the start of dynamic shared memory).
 struct SmemPlan {
   int V, Fp, G, cs, u, Xf, yf, gyf;
-  int sx, sxt, sg, sH, sA, sp;     // per slot: x, trial x, gradient, Hessian, Cholesky scratch, step
-  int e_mu, e_dmu, e_s2, e_tq, e_G, e_HC, e_HW, e_gh;  // per slot evaluation scratch
-  int sf, slam, spred, shs;        // per slot scalars
-  int bestx, misc, adj;            // [d] best candidate ; scalar/scratch area ; adjoint duals
-  int ints;                        // int area (in doubles)
-  int total;                       // total doubles
+  int sx, sxt, sg, sH, sA, sp;               // per slot: x, trial x, gradient, Hessian, Cholesky scratch, step
+  int sHt, sHref, sga, sdmu, sdsig, sgh;     // per slot: trial Hessian (-H alpha), reference H alpha, grad alpha, grad mu, grad sigma, scalars
+  int sf, slam, spred, shs;                  // per slot scalars
+  int ppre, ppost, phess;                    // partial sums of the row reductions
+  int bestx, misc, adj;                      // [d] best candidate ; scalar/scratch area ; adjoint duals
+  int pairs, tbl, ints;                      // int areas (in doubles)
+  int total;                                 // total doubles
 };
 
 __host__ __device__ inline int ncols_adjoint(int d) { return 4 * (d + 1) + 2; }
+__host__ __device__ inline int npairs_max(int d, int W) {
+  int q1 = d + 1, T = q1 * (q1 + 1) / 2 + 1, a = W * T, b = q1 * (2 * d + 3);
+  return a > b ? a : b;
+}
 
-__host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int RP, int NR) {
+__host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int RP, int NR, int RSmax, int NPmax) {
   SmemPlan p;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };  // keep 16-byte alignment
+  const int dd = d * d, q1 = d + 1, T2 = d * (d + 1) / 2;
   p.V = take(NR * RP);
   p.Fp = take((N8 + RBO_MAXFAN) * RBO_PR);
   p.G = take(RBO_MAXFAN * RBO_MAXFAN);
@@ -73,15 +80,18 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.Xf = take(RBO_MAXFAN * d);
   p.yf = take(RBO_MAXFAN);
   p.gyf = take(RBO_MAXFAN * d);
-  int dd = d * d;
   p.sx = take(W * d); p.sxt = take(W * d); p.sg = take(W * d); p.sH = take(W * dd); p.sA = take(W * dd); p.sp = take(W * d);
-  p.e_mu = take(W); p.e_dmu = take(W * d); p.e_s2 = take(W); p.e_tq = take(W * d);
-  p.e_G = take(W * dd); p.e_HC = take(W * dd); p.e_HW = take(W * dd); p.e_gh = take(W * 8);
+  p.sHt = take(W * dd); p.sHref = take(W * dd); p.sga = take(W * d); p.sdmu = take(W * d); p.sdsig = take(W * d); p.sgh = take(W * 8);
   p.sf = take(W); p.slam = take(W); p.spred = take(W); p.shs = take(W);
+  p.ppre = take(RSmax * W * q1);
+  p.ppost = take(RSmax * NPmax);
+  p.phess = take(RSmax * W * 2 * (T2 + 1));
   p.bestx = take(d);
-  p.misc = take(64 + 4 * (d + 1) * (d + 1) + 8 * d);
+  p.misc = take(64 + 2 * q1 * q1);
   p.adj = take(19 * d + 32);
-  p.ints = take(64 + 8 * W + ncols_adjoint(d) + W * (d + 1));
+  p.pairs = take((NPmax + 1) / 2);
+  p.tbl = take((q1 * (q1 + 1) / 2 + T2 + 2) / 2 + 1);
+  p.ints = take(64 + 10 * W + 32 * W / 2 + (ncols_adjoint(d) + W * q1 + 1) / 2);
   p.total = o;
   return p;
 }
