@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librbo.so")
+LIB_PATH = os.environ.get("RBO_LIB_PATH", os.path.join(_HERE, "csrc", "librbo.so"))  # override = development aid (timer build)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

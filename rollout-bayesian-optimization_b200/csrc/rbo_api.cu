@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -35,7 +36,7 @@ struct rbo_handle {
   rbo_solver_opts so;
   // surrogate
   bool have_sur = false;
-  int d = 0, N = 0, N8 = 0, nb8 = 0;
+  int d = 0, N = 0, N8 = 0, nb8 = 0, nb32 = 0;
   KernelSpec kern;
   int rule_id = 0;
   double sigma_tol = 1e-8, sigma_n2 = 1e-6, k0 = 1, d2k0 = 0, ymin_base = 0;
@@ -53,8 +54,8 @@ struct rbo_handle {
   int* work_counter = nullptr;
   double* sums = nullptr;
   int sums_len = 0;
-  double *dual_dirs = nullptr, *x_forced = nullptr;
-  size_t dual_cap = 0, forced_cap = 0;
+  double *dual_dirs = nullptr, *x_forced = nullptr, *cs_tape = nullptr;
+  size_t dual_cap = 0, forced_cap = 0, tape_cap = 0;
   // last call
   int last_h = 0, last_mode = 0, last_nth = 1;
   bool tape_enabled = true;
@@ -143,7 +144,7 @@ int rbo_destroy(rbo_handle* h) {
   cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->Xb, h->yb, h->c0, h->u0, h->Lf, h->Lb, h->rn, h->starts, h->sobol_dirs, h->values, h->grad_x, h->grad_theta, h->xs, h->ys,
                   h->gys, h->alphas, h->best_index, h->grad_case, h->status, h->n_evals, h->start_status, h->start_iters, h->work_counter, h->sums,
-                  h->dual_dirs, h->x_forced};
+                  h->dual_dirs, h->x_forced, h->cs_tape};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -203,29 +204,34 @@ int rbo_set_surrogate(rbo_handle* h, int d, int N, const double* X, int ldX, con
     for (int k = 0; k < i; ++k) s -= Lij(i, k) * u0[k];
     u0[i] = s / Lij(i, i);
   }
-  // forward / backward panels with inverted 8x8 diagonal blocks
-  const size_t nLf = (size_t)32 * nb8 * (nb8 + 1), nLb = (size_t)8 * N8 * nb8 - (size_t)32 * nb8 * (nb8 - 1);
+  // forward / backward 32-row panels with inverted diagonal blocks, k-major with pitch RBO_LP:
+  //   forward  panel ib: k = 0 .. 32 ib - 1 : L[32 ib + r][k]          ; then kk = 0..31 : Dinv_ib[r][kk]
+  //   backward panel ib: k' = 0 .. N32 - 32 (ib+1) - 1 : L[32 (ib+1) + k'][32 ib + r] ; then kk : Dinv_ib[kk][r]
+  const int BR = RBO_BR, LP = RBO_LP, nb32 = (N + BR - 1) / BR, N32 = nb32 * BR;
+  h->nb32 = nb32;
+  const size_t nLf = (size_t)LP * BR * ((size_t)nb32 * (nb32 + 1) / 2), nLb = nLf;
   std::vector<double> Lf(nLf, 0.0), Lb(nLb, 0.0);
-  for (int ib = 0; ib < nb8; ++ib) {
-    double Dinv[8][8];
-    for (int cc = 0; cc < 8; ++cc)
-      for (int rr = 0; rr < 8; ++rr) {
+  std::vector<double> Dinv((size_t)BR * BR);
+  for (int ib = 0; ib < nb32; ++ib) {
+    const int r0 = BR * ib;
+    for (int cc = 0; cc < BR; ++cc)
+      for (int rr = 0; rr < BR; ++rr) {
         double t = (rr == cc) ? 1.0 : 0.0;
-        for (int j = cc; j < rr; ++j) t -= Lij(8 * ib + rr, 8 * ib + j) * Dinv[j][cc];
-        Dinv[rr][cc] = (rr < cc) ? 0.0 : t / Lij(8 * ib + rr, 8 * ib + rr);
+        for (int j = cc; j < rr; ++j) t -= Lij(r0 + rr, r0 + j) * Dinv[(size_t)j * BR + cc];
+        Dinv[(size_t)rr * BR + cc] = (rr < cc) ? 0.0 : t / Lij(r0 + rr, r0 + rr);
       }
-    double* pf = Lf.data() + (size_t)32 * ib * (ib + 1);
-    const int nk = 8 * ib;
+    double* pf = Lf.data() + (size_t)LP * BR * ((size_t)ib * (ib + 1) / 2);
+    const int nk = BR * ib;
     for (int k = 0; k < nk; ++k)
-      for (int r = 0; r < 8; ++r) pf[(size_t)k * 8 + r] = (8 * ib + r < N) ? Lij(8 * ib + r, k) : 0.0;
-    for (int kk = 0; kk < 8; ++kk)
-      for (int r = 0; r < 8; ++r) pf[(size_t)(nk + kk) * 8 + r] = Dinv[r][kk];
-    double* pb = Lb.data() + ((size_t)8 * N8 * ib - (size_t)32 * ib * (ib - 1));
-    const int k0 = 8 * (ib + 1), nkb = N8 - k0;
+      for (int r = 0; r < BR; ++r) pf[(size_t)k * LP + r] = (r0 + r < N) ? Lij(r0 + r, k) : 0.0;
+    for (int kk = 0; kk < BR; ++kk)
+      for (int r = 0; r < BR; ++r) pf[(size_t)(nk + kk) * LP + r] = Dinv[(size_t)r * BR + kk];
+    double* pb = Lb.data() + (size_t)LP * BR * ((size_t)nb32 * ib - (size_t)ib * (ib - 1) / 2);
+    const int k0 = BR * (ib + 1), nkb = N32 - k0;
     for (int kk = 0; kk < nkb; ++kk)
-      for (int r = 0; r < 8; ++r) pb[(size_t)kk * 8 + r] = (k0 + kk < N && 8 * ib + r < N) ? Lij(k0 + kk, 8 * ib + r) : 0.0;
-    for (int kk = 0; kk < 8; ++kk)
-      for (int r = 0; r < 8; ++r) pb[(size_t)(nkb + kk) * 8 + r] = Dinv[kk][r];
+      for (int r = 0; r < BR; ++r) pb[(size_t)kk * LP + r] = (k0 + kk < N && r0 + r < N) ? Lij(k0 + kk, r0 + r) : 0.0;
+    for (int kk = 0; kk < BR; ++kk)
+      for (int r = 0; r < BR; ++r) pb[(size_t)(nkb + kk) * LP + r] = Dinv[(size_t)kk * BR + r];
   }
   CK(h, dev_realloc(&h->Xb, Xb.size()));
   CK(h, dev_realloc(&h->yb, (size_t)N));
@@ -322,19 +328,21 @@ static int ensure_outputs(rbo_handle* h, int M, int hor, int S, int d, int nth) 
 }
 
 // Chooses the number of start slots W (starts evaluated in lock-step) so that the shared-memory plan fits.
-struct PlanChoice { int W, RP, NR, RSmax, NPmax; size_t bytes; };
+struct PlanChoice { int W, RP, NR, RSmax, NPmax, xsm; size_t bytes; };
 static bool choose_plan(const rbo_handle* h, int hor, int S, PlanChoice* pc) {
-  const int d = h->d, N8 = h->N8, CS = d + 3, NR = N8 + RBO_MAXFAN;
+  const int d = h->d, N8 = h->N8, CS = d + 3, NR = std::max(N8 + RBO_MAXFAN, h->nb32 * RBO_BR);
   const int nadj = ncols_adjoint(d);
   for (int W = std::min(S, RBO_NWARPS); W >= 1; --W) {
     // prefer a W that divides the start list into equal passes (fewer idle slots at the tail)
     int RP = std::max(W * CS, nadj) + 2;
     if ((RP & 1) == 0) RP += 1;  // odd pitch: conflict-free column walks
-    for (int RSmax = 4; RSmax >= 1; RSmax >>= 1) {
+    // preference order: keep the base locations in shared memory, then more row splits
+    const int tries[4][2] = {{2, 1}, {1, 1}, {2, 0}, {1, 0}};
+    for (auto& t : tries) {
       int NPmax = npairs_max(d, W);
-      SmemPlan pl = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax);
+      SmemPlan pl = make_plan(d, N8, hor, W, RP, NR, t[0], NPmax, t[1]);
       size_t bytes = (size_t)pl.total * 8;
-      if (bytes <= (size_t)h->max_smem) { *pc = {W, RP, NR, RSmax, NPmax, bytes}; return true; }
+      if (bytes <= (size_t)h->max_smem) { *pc = {W, RP, NR, t[0], NPmax, t[1], bytes}; return true; }
     }
   }
   return false;
@@ -365,11 +373,12 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   PlanChoice pc;
   if (!choose_plan(h, horizon, S, &pc))
     return fail(h, RBO_ERR_UNSUPPORTED, "rbo_rollout: problem (d=%d, N=%d, h=%d) needs more than %d bytes of shared memory per CTA", h->d, h->N, horizon, h->max_smem);
+  if (getenv("RBO_DEBUG")) fprintf(stderr, "[rbo] plan: W=%d RP=%d NR=%d RSmax=%d NPmax=%d xsm=%d smem=%zu B (limit %d)\n", pc.W, pc.RP, pc.NR, pc.RSmax, pc.NPmax, pc.xsm, pc.bytes, h->max_smem);
   int rc = ensure_outputs(h, M, horizon, S, h->d, ntheta);
   if (rc) return rc;
   DevProblem P;
   memset(&P, 0, sizeof(P));
-  P.d = h->d; P.N = h->N; P.N8 = h->N8; P.nb8 = h->nb8; P.h = horizon; P.S = S; P.W = pc.W; P.RSmax = pc.RSmax; P.NPmax = pc.NPmax;
+  P.d = h->d; P.N = h->N; P.N8 = h->N8; P.nb8 = h->nb8; P.nb32 = h->nb32; P.h = horizon; P.S = S; P.W = pc.W; P.RSmax = pc.RSmax; P.NPmax = pc.NPmax; P.xsm = pc.xsm; P.XP = h->N8 + 1;
   P.CS = h->d + 3; P.RP = pc.RP; P.NR = pc.NR; P.M = M; P.hp1 = h->hp1; P.mode = mode; P.flags = flags; P.ntheta = ntheta;
   P.kern = h->kern; P.rule_id = h->rule_id; P.sigma_tol = h->sigma_tol; P.sigma_n2 = h->sigma_n2; P.k0 = h->k0; P.d2k0 = h->d2k0;
   P.ymin_base = h->ymin_base; P.fmini = fmini; P.theta1 = theta[0]; P.htol = h->htol; P.so = h->so;
@@ -381,6 +390,11 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   P.start_status = h->tape_enabled ? h->start_status : nullptr; P.start_iters = h->tape_enabled ? h->start_iters : nullptr;
   P.work_counter = h->work_counter;
   const int grid = std::min(M, h->num_sms);
+  {
+    size_t need = (size_t)grid * (horizon + 2) * pc.NR;
+    if (h->tape_cap < need) { CK(h, dev_realloc(&h->cs_tape, need)); h->tape_cap = need; }
+    P.cs_tape = h->cs_tape;
+  }
   CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
   CK(h, cudaEventRecord(h->ev0, h->stream));
   rbo_rollout_kernel<<<grid, RBO_THREADS, pc.bytes, h->stream>>>(P);
@@ -581,6 +595,8 @@ int rbo_multistart_base_solve(rbo_handle* h, const double* theta, int ntheta, co
 }
 
 int rbo_num_sms(const rbo_handle* h) { return h ? h->num_sms : 0; }
+
+
 
 int rbo_fp64_peak(rbo_handle* h, double* tflops) {
   if (!h || !tflops) return RBO_ERR_ARG;

@@ -10,8 +10,13 @@
 #define RBO_MAXD 32      // max input dimension d
 #define RBO_THREADS 512  // threads per CTA of the rollout kernel
 #define RBO_NWARPS (RBO_THREADS / 32)
+#define RBO_NCONS (RBO_NWARPS - 1)  // consumer warps of the panel pipeline; warp RBO_NCONS is the TMA producer
 #define RBO_PR 8         // rows per factor panel
 #define RBO_MAXFAN 8     // fantasy rows per trajectory (h + 1 <= 8)
+#define RBO_BR 32        // rows per packed L0 panel (block row of the blocked triangular solve)
+#define RBO_LP 36        // doubles per k in a packed L0 panel: 32 rows + 4 pad (288-byte pitch)
+#define RBO_CHUNK_K 32   // k-values per staged panel chunk (32 * 288 B = 9216 B per bulk copy); == RBO_BR
+#define RBO_NSTAGE 3     // stages of the panel ring buffer
 #define RBO_FLAG_MYOPIC_INTERNAL (1 << 16)  // kernel-internal: myopic multistart against the base surrogate
 
 namespace rbo {

@@ -8,9 +8,11 @@ namespace rbo {
 struct DevProblem {
   // sizes
   int d, N, N8, nb8;      // input dim; base observations; N rounded up to RBO_PR; N8 / RBO_PR
+  int nb32;               // number of 32-row panels of L0 (ceil(N / RBO_BR))
   int h, S, W;            // horizon; start columns; start slots evaluated together in one lock-step round
   int CS, RP, NR;         // columns per start slot (d+3); padded V row pitch (doubles); V rows (N8 + RBO_MAXFAN)
   int RSmax, NPmax;       // row splits of the reductions; capacity of the pair list
+  int xsm, XP;            // base locations staged in shared memory (1) or read through L1 (0); their row pitch
   int M;                  // trajectories owned by this handle
   int hp1;                // third dimension of the normals tensor
   int mode, flags, ntheta;
@@ -47,11 +49,12 @@ struct DevProblem {
   int* start_status;   // [M][h][S]
   int* start_iters;    // [M][h][S]
   int* work_counter;   // dynamic trajectory scheduler
+  double* cs_tape;     // [gridDim.x][h+2][NR] coefficient tape of the trajectory each CTA is working on
 };
 
 // Shared-memory plan (offsets in doubles from the start of dynamic shared memory).
 struct SmemPlan {
-  int V, Fp, G, cs, u, Xf, yf, gyf;
+  int V, Fp, G, u, Xf, yf, gyf, Xs, stage, mbar;
   int sx, sxt, sg, sH, sA, sp;               // per slot: x, trial x, gradient, Hessian, Cholesky scratch, step
   int sHt, sHref, sga, sdmu, sdsig, sgh;     // per slot: trial Hessian (-H alpha), reference H alpha, grad alpha, grad mu, grad sigma, scalars
   int sf, slam, spred, shs;                  // per slot scalars
@@ -63,11 +66,11 @@ struct SmemPlan {
 
 __host__ __device__ inline int ncols_adjoint(int d) { return 4 * (d + 1) + 2; }
 __host__ __device__ inline int npairs_max(int d, int W) {
-  int q1 = d + 1, T = q1 * (q1 + 1) / 2 + 1, a = W * T, b = q1 * (2 * d + 3);
+  int q1 = d + 1, a = W * q1 * q1, b = 2 * q1 * q1 + 2 * q1;  // outputs of the largest column-product call
   return a > b ? a : b;
 }
 
-__host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int RP, int NR, int RSmax, int NPmax) {
+__host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int RP, int NR, int RSmax, int NPmax, int xsm) {
   SmemPlan p;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };  // keep 16-byte alignment
@@ -75,11 +78,13 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.V = take(NR * RP);
   p.Fp = take((N8 + RBO_MAXFAN) * RBO_PR);
   p.G = take(RBO_MAXFAN * RBO_MAXFAN);
-  p.cs = take((h + 2) * NR);
   p.u = take(NR);
   p.Xf = take(RBO_MAXFAN * d);
   p.yf = take(RBO_MAXFAN);
   p.gyf = take(RBO_MAXFAN * d);
+  p.Xs = take(xsm ? d * (N8 + 1) : 0);
+  p.stage = take(RBO_NSTAGE * RBO_CHUNK_K * RBO_LP);
+  p.mbar = take(2 * RBO_NSTAGE + 2);
   p.sx = take(W * d); p.sxt = take(W * d); p.sg = take(W * d); p.sH = take(W * dd); p.sA = take(W * dd); p.sp = take(W * d);
   p.sHt = take(W * dd); p.sHref = take(W * dd); p.sga = take(W * d); p.sdmu = take(W * d); p.sdsig = take(W * d); p.sgh = take(W * 8);
   p.sf = take(W); p.slam = take(W); p.spred = take(W); p.shs = take(W);
@@ -89,8 +94,8 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.bestx = take(d);
   p.misc = take(64 + 2 * q1 * q1);
   p.adj = take(19 * d + 32);
-  p.pairs = take((NPmax + 1) / 2);
-  p.tbl = take((q1 * (q1 + 1) / 2 + T2 + 2) / 2 + 1);
+  p.pairs = take((5 * (W + 2) + 1) / 2);  // product items
+  p.tbl = take((T2 + 2) / 2 + 1);
   p.ints = take(64 + 10 * W + 32 * W / 2 + (ncols_adjoint(d) + W * q1 + 1) / 2);
   p.total = o;
   return p;

@@ -19,6 +19,15 @@
 
 namespace rbo {
 
+#ifdef RBO_PHASE_TIMERS
+__device__ unsigned long long g_phase_cycles[16];
+#define PT_DECL long long pt_t0 = clock64()
+#define PT_MARK(i) do { if (threadIdx.x == 0) { long long t1_ = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(t1_ - pt_t0)); pt_t0 = t1_; } } while (0)
+#else
+#define PT_DECL
+#define PT_MARK(i)
+#endif
+
 namespace {
 
 // int-area layout
@@ -51,41 +60,43 @@ struct K {
   int tid, lane, warp;
   int nf;  // number of fantasy rows that are active for the current operation (uniform over the CTA)
   int CCOL, UCOL;  // columns of V that hold the current coefficients c and u = L^-1 y
-  double *V, *Fp, *G, *cs, *u, *Xf, *yf, *gyf, *misc, *adj, *bestx;
-  int *alist, *phase, *sstat, *siter, *stry, *sstart, *sevals, *sfr, *colidx, *pairs, *tblq, *tbld;
+  double *V, *Fp, *G, *u, *Xf, *yf, *gyf, *misc, *adj, *bestx, *Xs, *stage;
+  double* cst;     // this CTA's coefficient tape in global memory: cst[k * NR + j] = cs[k][j] (rbs.jl:326)
+  unsigned long long* mbar;
+  unsigned qglob;  // running count of staged panel chunks (ring position and mbarrier parity)
+  int *alist, *phase, *sstat, *siter, *stry, *sstart, *sevals, *sfr, *colidx, *items, *tbld;
 
   __device__ K(const DevProblem& P_, double* sm_) : P(P_), sm(sm_) {
-    pl = make_plan(P.d, P.N8, P.h, P.W, P.RP, P.NR, P.RSmax, P.NPmax);
+    pl = make_plan(P.d, P.N8, P.h, P.W, P.RP, P.NR, P.RSmax, P.NPmax, P.xsm);
     tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
     nf = 0;
     CCOL = P.RP - 1; UCOL = P.RP - 2;
-    V = sm + pl.V; Fp = sm + pl.Fp; G = sm + pl.G; cs = sm + pl.cs; u = sm + pl.u;
+    V = sm + pl.V; Fp = sm + pl.Fp; G = sm + pl.G; u = sm + pl.u; Xs = sm + pl.Xs; stage = sm + pl.stage;
+    mbar = reinterpret_cast<unsigned long long*>(sm + pl.mbar); qglob = 0;
+    cst = P.cs_tape + (size_t)blockIdx.x * (P.h + 2) * P.NR;
     Xf = sm + pl.Xf; yf = sm + pl.yf; gyf = sm + pl.gyf; misc = sm + pl.misc; adj = sm + pl.adj; bestx = sm + pl.bestx;
     si = reinterpret_cast<int*>(sm + pl.ints);
-    pairs = reinterpret_cast<int*>(sm + pl.pairs);
-    tblq = reinterpret_cast<int*>(sm + pl.tbl);
-    const int W = P.W, q1 = P.d + 1;
-    tbld = tblq + q1 * (q1 + 1) / 2;
+    items = reinterpret_cast<int*>(sm + pl.pairs);
+    tbld = reinterpret_cast<int*>(sm + pl.tbl);
+    const int W = P.W;
     alist = si + I_ARR; phase = alist + W; sstat = phase + W; siter = sstat + W; stry = siter + W;
     sstart = stry + W; sevals = sstart + W; sfr = sevals + W; colidx = sfr + 32 * W;
   }
 
   __device__ __forceinline__ double xcoord(int j, int p) const {
-    return j < P.N8 ? __ldg(P.Xb + (size_t)p * P.N8 + j) : Xf[(j - P.N8) * P.d + p];
+    return j < P.N8 ? (P.xsm ? Xs[p * P.XP + j] : __ldg(P.Xb + (size_t)p * P.N8 + j)) : Xf[(j - P.N8) * P.d + p];
   }
   __device__ __forceinline__ bool row_active(int j) const { return j < P.N || (j >= P.N8 && j < P.N8 + nf); }
   __device__ __forceinline__ int nact_rows() const { return P.N + nf; }
   __device__ __forceinline__ int act_row(int a) const { return a < P.N ? a : P.N8 + (a - P.N); }
 
-  // (p, q) tables of the upper triangles of size d+1 (tblq) and d (tbld), packed p | q << 8
+  // (p, q) table of the upper triangle of size d, packed p | q << 8
   __device__ void build_tables() {
-    const int d = P.d, q1 = d + 1;
-    for (int e = tid; e < q1 * (q1 + 1) / 2 + d * (d + 1) / 2; e += RBO_THREADS) {
-      int n = q1, t = e;
-      if (e >= q1 * (q1 + 1) / 2) { n = d; t = e - q1 * (q1 + 1) / 2; }
-      int p = 0;
-      while (t >= n - p) { t -= n - p; ++p; }
-      tblq[e] = p | ((p + t) << 8);
+    const int d = P.d;
+    for (int e = tid; e < d * (d + 1) / 2; e += RBO_THREADS) {
+      int p = 0, t = e;
+      while (t >= d - p) { t -= d - p; ++p; }
+      tbld[e] = p | ((p + t) << 8);
     }
   }
 
@@ -121,123 +132,189 @@ struct K {
   }
 
   // ------------------------------------------------------------------------------------------------
-  // Row reductions.  out[rs * npairs + i] = sum over the rows of split rs of V[j][c1_i] * V[j][c2_i], pairs[i] =
-  // c1 | c2 << 16.  A warp owns a block of 72 pairs and one row split; lane = (row group rg = lane & 3, pair group
-  // eg = lane >> 2): 9 accumulators per lane, rows a = rg + 4 * (rs + RS * i). The RS partial sums are added in a
-  // fixed order by the consumer, so results do not depend on scheduling.
+  // Row reductions on the FP64 tensor cores.
+  //   colprod: for every product item {colA, na, colB, nb, out}: out[rs][p * nb + q] = sum over the rows of split rs of
+  //            V[j][colA + p] * V[j][colB + q]   (A' * B down the rows; 16 x 16 output blocks, 4 rows per DMMA step).
+  //   hess_sums: HC = sum_j c_j Hk(x - X_j), HW = sum_j w_j Hk(x - X_j) for np points, r = x - X_j built on the fly.
+  // A warp-task = (item, output block, row split); the RS partial sums are added in a fixed order by the consumer, so
+  // results do not depend on scheduling.
   // ------------------------------------------------------------------------------------------------
   __device__ int choose_rs(int nblocks) const {
     int rs = RBO_NWARPS / (nblocks > 0 ? nblocks : 1);
     return rs < 1 ? 1 : (rs > P.RSmax ? P.RSmax : rs);
   }
+  __device__ __forceinline__ void set_item(int i, int colA, int na, int colB, int nb, int out) {
+    int* it = items + 5 * i;
+    it[0] = colA; it[1] = na; it[2] = colB; it[3] = nb; it[4] = out;
+  }
+  __device__ static __forceinline__ int nblk16(int n) { return (n + 15) >> 4; }
 
-  __device__ void reduce_pairs(int npairs, double* out, int RS) {
-    const int RP = P.RP, na = nact_rows(), rg = lane & 3, eg = lane >> 2;
-    const int nblk = (npairs + 71) / 72;
-    for (int task = warp; task < nblk * RS; task += RBO_NWARPS) {
-      const int blk = task / RS, rs = task - blk * RS;
-      int c1[9], c2[9];
-      double acc[9];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        int e = blk * 72 + eg * 9 + i;
-        int pr = e < npairs ? pairs[e] : 0;
-        c1[i] = pr & 0xffff; c2[i] = pr >> 16;
-        acc[i] = 0.0;
+  // dst[rs * nout + item.out + p * nb + q]; nout = total number of outputs of this call (stride between row splits)
+  __device__ void colprod(int nitems, int nout, double* dst, int RS) {
+    const int RP = P.RP, nrows = P.N8 + nf, g = lane >> 2, tg = lane & 3;
+    int ntask = 0;
+    for (int i = 0; i < nitems; ++i) ntask += nblk16(items[5 * i + 1]) * nblk16(items[5 * i + 3]);
+    for (int task = warp; task < ntask * RS; task += RBO_NWARPS) {
+      int t = task / RS;
+      const int rs = task - t * RS;
+      int i = 0, nbA, nbB;
+      for (;; ++i) { nbA = nblk16(items[5 * i + 1]); nbB = nblk16(items[5 * i + 3]); if (t < nbA * nbB) break; t -= nbA * nbB; }
+      const int* it = items + 5 * i;
+      const int colA = it[0], na = it[1], colB = it[2], nb = it[3], mb = t / nbB, nk = t - mb * nbB;
+      const int ca0 = colA + min(16 * mb + g, na - 1), ca1 = colA + min(16 * mb + 8 + g, na - 1);
+      const int cb0 = colB + min(16 * nk + g, nb - 1), cb1 = colB + min(16 * nk + 8 + g, nb - 1);
+      double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+      for (int j0 = 4 * rs; j0 < nrows; j0 += 4 * RS) {
+        const int j = j0 + tg;
+        const bool in = j < nrows;
+        const double* row = V + (size_t)(in ? j : 0) * RP;
+        const double a0 = in ? row[ca0] : 0.0, a1 = in ? row[ca1] : 0.0, b0 = in ? row[cb0] : 0.0, b1 = in ? row[cb1] : 0.0;
+        dmma(c00[0], c00[1], a0, b0);
+        dmma(c01[0], c01[1], a0, b1);
+        dmma(c10[0], c10[1], a1, b0);
+        dmma(c11[0], c11[1], a1, b1);
       }
-      for (int a = rg + 4 * rs; a < na; a += 4 * RS) {
-        const double* row = V + (size_t)act_row(a) * RP;
+      double* o = dst + (size_t)rs * nout + it[4];
+      const int p0 = 16 * mb + g, p1 = p0 + 8, q0 = 16 * nk + 2 * tg, q1_ = q0 + 8;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) acc[i] = fma(row[c1[i]], row[c2[i]], acc[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        acc[i] += __shfl_xor_sync(FULL, acc[i], 1);
-        acc[i] += __shfl_xor_sync(FULL, acc[i], 2);
-      }
-      if (rg == 0) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          int e = blk * 72 + eg * 9 + i;
-          if (e < npairs) out[(size_t)rs * npairs + e] = acc[i];
-        }
+      for (int e = 0; e < 2; ++e) {
+        if (p0 < na && q0 + e < nb) o[p0 * nb + q0 + e] = c00[e];
+        if (p0 < na && q1_ + e < nb) o[p0 * nb + q1_ + e] = c01[e];
+        if (p1 < na && q0 + e < nb) o[p1 * nb + q0 + e] = c10[e];
+        if (p1 < na && q1_ + e < nb) o[p1 * nb + q1_ + e] = c11[e];
       }
     }
   }
 
-  // HC = sum_j c_j Hk(x - X_j) (rbs.jl:516-523) and HW = sum_j w_j Hk(x - X_j) (rbs.jl:542-545) for np points.
-  // Hk = a r r' + b I: entries (p <= q) accumulate a r_p r_q, the b-weighted sums go to the extra entry T2.
-  // phess[((rs * np + s) * 2 + which) * (T2 + 1) + e], which = 0 (c-weighted) / 1 (w-weighted).
+  // Hk = a r r' + b I (rbf.jl:141-150): entries (p <= q) accumulate a r_p r_q, the b-weighted sums go to the extra entry T2.
+  // phess[((rs * np + s) * 2 + which) * (T2 + 1) + e], which = 0 (c-weighted, rbs.jl:516-523) / 1 (w-weighted, rbs.jl:542-545).
   // Columns: (a, b) at cab(s) + d+1, d+2 ; w at cw(s) ; c in CCOL.
   template <class PT, class CAB, class CW>
-  __device__ void reduce_hess(int np, PT pt, CAB cab, CW cw, int RS) {
-    const int d = P.d, RP = P.RP, T2 = d * (d + 1) / 2, na = nact_rows(), rg = lane & 3, eg = lane >> 2;
-    const int nblk = (T2 + 55) / 56;
+  __device__ void hess_sums(int np, PT pt, CAB cab, CW cw, int RS) {
+    const int d = P.d, RP = P.RP, T2 = d * (d + 1) / 2, nrows = P.N8 + nf, g = lane >> 2, tg = lane & 3;
+    const int nbd = nblk16(d), nblk = nbd * (nbd + 1) / 2;  // upper-triangular 16 x 16 blocks
     double* out = sm + pl.phess;
     for (int task = warp; task < np * nblk * RS; task += RBO_NWARPS) {
       const int s = task / (nblk * RS), rem = task - s * nblk * RS, blk = rem / RS, rs = rem - blk * RS;
+      int mb = 0, t = blk;
+      while (t >= nbd - mb) { t -= nbd - mb; ++mb; }
+      const int nk = mb + t;
       const double* x = pt(s);
       const int colab = cab(s) + d + 1, colw = cw(s);
-      int pp[7], qq[7];
-      double xp[7], xq[7], accC[7], accW[7], bC = 0.0, bW = 0.0;
+      const int p0 = min(16 * mb + g, d - 1), p1 = min(16 * mb + 8 + g, d - 1), q0 = min(16 * nk + g, d - 1), q1_ = min(16 * nk + 8 + g, d - 1);
+      const double xp0 = x[p0], xp1 = x[p1], xq0 = x[q0], xq1 = x[q1_];
+      double cC[4][2], cW[4][2], bC = 0.0, bW = 0.0;
 #pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        int e = blk * 56 + eg * 7 + i;
-        int pq = e < T2 ? tbld[e] : 0;
-        pp[i] = pq & 0xff; qq[i] = pq >> 8;
-        xp[i] = x[pp[i]]; xq[i] = x[qq[i]];
-        accC[i] = 0.0; accW[i] = 0.0;
-      }
-      for (int a = rg + 4 * rs; a < na; a += 4 * RS) {
-        const int j = act_row(a);
-        const double* row = V + (size_t)j * RP;
-        const double aj = row[colab], bj = row[colab + 1], wj = row[colw], cj = row[CCOL];
+      for (int i = 0; i < 4; ++i) { cC[i][0] = cC[i][1] = 0.0; cW[i][0] = cW[i][1] = 0.0; }
+      for (int j0 = 4 * rs; j0 < nrows; j0 += 4 * RS) {
+        const int j = j0 + tg;
+        const bool in = j < nrows;
+        const int jj = in ? j : 0;
+        const double* row = V + (size_t)jj * RP;
+        const double aj = in ? row[colab] : 0.0, bj = in ? row[colab + 1] : 0.0, wj = row[colw], cj = row[CCOL];
         const double ca = cj * aj, wa = wj * aj;
-        bC = fma(cj, bj, bC); bW = fma(wj, bj, bW);
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-          double rr = (xp[i] - xcoord(j, pp[i])) * (xq[i] - xcoord(j, qq[i]));
-          accC[i] = fma(ca, rr, accC[i]);
-          accW[i] = fma(wa, rr, accW[i]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        accC[i] += __shfl_xor_sync(FULL, accC[i], 1); accC[i] += __shfl_xor_sync(FULL, accC[i], 2);
-        accW[i] += __shfl_xor_sync(FULL, accW[i], 1); accW[i] += __shfl_xor_sync(FULL, accW[i], 2);
+        const double rp0 = xp0 - xcoord(jj, p0), rp1 = xp1 - xcoord(jj, p1), rq0 = xq0 - xcoord(jj, q0), rq1 = xq1 - xcoord(jj, q1_);
+        if (g == 0) { bC = fma(cj, bj, bC); bW = fma(wj, bj, bW); }
+        dmma(cC[0][0], cC[0][1], ca * rp0, rq0);
+        dmma(cC[1][0], cC[1][1], ca * rp0, rq1);
+        dmma(cC[2][0], cC[2][1], ca * rp1, rq0);
+        dmma(cC[3][0], cC[3][1], ca * rp1, rq1);
+        dmma(cW[0][0], cW[0][1], wa * rp0, rq0);
+        dmma(cW[1][0], cW[1][1], wa * rp0, rq1);
+        dmma(cW[2][0], cW[2][1], wa * rp1, rq0);
+        dmma(cW[3][0], cW[3][1], wa * rp1, rq1);
       }
       bC += __shfl_xor_sync(FULL, bC, 1); bC += __shfl_xor_sync(FULL, bC, 2);
       bW += __shfl_xor_sync(FULL, bW, 1); bW += __shfl_xor_sync(FULL, bW, 2);
-      if (rg == 0) {
-        double* oC = out + ((size_t)(rs * np + s) * 2 + 0) * (T2 + 1);
-        double* oW = out + ((size_t)(rs * np + s) * 2 + 1) * (T2 + 1);
+      double* oC = out + ((size_t)(rs * np + s) * 2 + 0) * (T2 + 1);
+      double* oW = out + ((size_t)(rs * np + s) * 2 + 1) * (T2 + 1);
 #pragma unroll
-        for (int i = 0; i < 7; ++i) {
-          int e = blk * 56 + eg * 7 + i;
-          if (e < T2) { oC[e] = accC[i]; oW[e] = accW[i]; }
+      for (int i = 0; i < 4; ++i) {
+        const int p = 16 * mb + 8 * (i >> 1) + g;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int q = 16 * nk + 8 * (i & 1) + 2 * tg + e;
+          if (p <= q && q < d) { const int idx = tri_idx(p, q, d); oC[idx] = cC[i][e]; oW[idx] = cW[i][e]; }
         }
-        if (blk == 0 && eg == 0) { oC[T2] = bC; oW[T2] = bW; }
       }
+      if (blk == 0 && lane == 0) { oC[T2] = bC; oW[T2] = bW; }
     }
   }
 
   // ------------------------------------------------------------------------------------------------
-  // Triangular solves of `ncols` columns of V (indices in colidx[]) against L = [L0 0; F G]:
-  // FWD: V <- L^-1 V, else V <- L^-T V.  A group of KS adjacent lanes owns one column and splits the
-  // k-range of every 8-row panel; partial sums are combined with xor-shuffles, the 8x8 diagonal blocks are
-  // pre-inverted so the diagonal step is a small mat-vec.  L0 panels come from global memory (read-only path),
-  // the fantasy panel from shared memory.  `nfan` = number of active fantasy rows.
+  // Triangular solves of `ncols` (<= RBO_THREADS) columns of V (indices in colidx[]) against L = [L0 0; F G]:
+  // FWD: V <- L^-1 V, else V <- L^-T V.
+  //  * L0 lives in global memory as 8-row panels (pitch RBO_LP doubles per k, 8x8 diagonal blocks pre-inverted). The
+  //    panels are streamed ONCE per solve into a 3-stage shared-memory ring with TMA bulk copies
+  //    (cp.async.bulk + mbarrier complete_tx), issued two chunks ahead by thread 0; every warp consumes the same chunk.
+  //  * A group of KS adjacent lanes owns one column and splits the k-range of every panel; partial sums are combined
+  //    with xor-shuffles, the diagonal step is a small mat-vec with the inverted block.
+  //  * The fantasy rows (<= 8, per trajectory) are one more panel that already sits in shared memory.
   // ------------------------------------------------------------------------------------------------
-  template <bool GLOBAL>
-  __device__ __forceinline__ void panel_rows(const double* pan, int nk, int part, int KS, const double* vcol, double acc[8]) const {
+  __device__ __forceinline__ unsigned smem_u32(const void* p) const { return (unsigned)__cvta_generic_to_shared(p); }
+
+  __device__ void mbar_init() {
+    if (tid == 0) {
+      for (int i = 0; i < RBO_NSTAGE; ++i) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[i])));                               // full: producer + tx bytes
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[RBO_NSTAGE + i])), "r"(RBO_NCONS));  // empty: one arrive per consumer warp
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __device__ __forceinline__ void chunk_issue(unsigned q, const double* src, int ndoubles) {  // one thread
+    const unsigned st = q % RBO_NSTAGE, mb = smem_u32(&mbar[st]), dst = smem_u32(stage + (size_t)st * RBO_CHUNK_K * RBO_LP);
+    const unsigned bytes = (unsigned)ndoubles * 8u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
+  }
+  __device__ __forceinline__ void mbar_wait(unsigned mb, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(mb), "r"(parity) : "memory");
+  }
+  __device__ __forceinline__ void full_wait(unsigned q) { mbar_wait(smem_u32(&mbar[q % RBO_NSTAGE]), (q / RBO_NSTAGE) & 1u); }
+  __device__ __forceinline__ void empty_wait(unsigned q) {  // producer: stage of chunk q was released by all consumers of chunk q - NSTAGE
+    mbar_wait(smem_u32(&mbar[RBO_NSTAGE + q % RBO_NSTAGE]), ((q / RBO_NSTAGE) - 1u) & 1u);
+  }
+  __device__ __forceinline__ void empty_arrive(unsigned q) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&mbar[RBO_NSTAGE + q % RBO_NSTAGE])) : "memory");
+  }
+
+  // FP64 tensor-core tile: D(8x8) += A(8x4) * B(4x8). Lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2], C[l >> 2][2 (l & 3) + {0, 1}].
+  __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) const {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+  }
+
+  // One 32-k chunk of a 32-row panel against 8 columns owned by this warp: C[4 row tiles][8x8] += L[32 x 32k] * V[32k x 8].
+  // buf: staged chunk, k-major with pitch RBO_LP; vrow0: V row of chunk-relative k = 0; cB: this lane's B-fragment column offset.
+  __device__ __forceinline__ void mma_chunk(const double* buf, const double* vrow0, int cB, int g, int tg, double c[4][2]) const {
     const int RP = P.RP;
-#pragma unroll 4
-    for (int k = part; k < nk; k += KS) {
-      double v = vcol[(size_t)k * RP];
+    const double* vp = vrow0 + (size_t)tg * RP + cB;
+    const double* ap = buf + (size_t)tg * RBO_LP + g;
+#pragma unroll
+    for (int kt = 0; kt < RBO_CHUNK_K / 4; ++kt) {
+      const double b = vp[(size_t)(4 * kt) * RP];
+      const double a0 = ap[4 * kt * RBO_LP], a1 = ap[4 * kt * RBO_LP + 8], a2 = ap[4 * kt * RBO_LP + 16], a3 = ap[4 * kt * RBO_LP + 24];
+      dmma(c[0][0], c[0][1], a0, b);
+      dmma(c[1][0], c[1][1], a1, b);
+      dmma(c[2][0], c[2][1], a2, b);
+      dmma(c[3][0], c[3][1], a3, b);
+    }
+  }
+
+  // ---- 8-row fantasy panel (shared memory, pitch 8): 4 lanes own one column and split k ----
+  __device__ __forceinline__ void fan_rows(const double* pan, int kend, int part, const double* vcol, double acc[8]) const {
+    const int RP = P.RP;
+#pragma unroll 2
+    for (int k = part; k < kend; k += 4) {
+      const double v = vcol[(size_t)k * RP];
       const double2* lp = reinterpret_cast<const double2*>(pan + (size_t)k * 8);
-      double2 l0, l1, l2, l3;
-      if (GLOBAL) { l0 = __ldg(lp); l1 = __ldg(lp + 1); l2 = __ldg(lp + 2); l3 = __ldg(lp + 3); }
-      else { l0 = lp[0]; l1 = lp[1]; l2 = lp[2]; l3 = lp[3]; }
+      const double2 l0 = lp[0], l1 = lp[1], l2 = lp[2], l3 = lp[3];
       acc[0] = fma(l0.x, v, acc[0]); acc[1] = fma(l0.y, v, acc[1]);
       acc[2] = fma(l1.x, v, acc[2]); acc[3] = fma(l1.y, v, acc[3]);
       acc[4] = fma(l2.x, v, acc[4]); acc[5] = fma(l2.y, v, acc[5]);
@@ -245,115 +322,158 @@ struct K {
     }
   }
 
-  __device__ __forceinline__ void group_reduce(double acc[8], int KS) const {
-    for (int off = KS >> 1; off > 0; off >>= 1) {
-#pragma unroll
-      for (int r = 0; r < 8; ++r) acc[r] += shfl_xor_d(acc[r], off);
-    }
+  template <bool FWD>
+  __device__ __forceinline__ const double* pan_ptr(int ib) const {  // global address of panel ib (see rbo_set_surrogate)
+    const size_t chunk = (size_t)RBO_LP * RBO_BR;
+    return FWD ? P.Lf + chunk * ((size_t)ib * (ib + 1) / 2) : P.Lb + chunk * ((size_t)P.nb32 * ib - (size_t)ib * (ib - 1) / 2);
   }
 
-  // out rows r == part (mod KS): v_r = sum_kk D[kk*8 + r] * t[kk]; rows >= rmax are forced to 0.
-  template <bool GLOBAL>
-  __device__ __forceinline__ void diag_apply(const double* dg, const double t[8], int part, int KS, double* vout /* row 0 of the block */,
-                                              bool valid, int rmax) const {
-    const int RP = P.RP;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      if ((r & (KS - 1)) == part) {
-        double s = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          double dv = GLOBAL ? __ldg(dg + kk * 8 + r) : dg[kk * 8 + r];
-          s = fma(dv, t[kk], s);
-        }
-        if (r >= rmax) s = 0.0;
-        if (valid && part < 8) vout[(size_t)r * RP] = s;
-      }
-    }
-  }
-
+  // Triangular solves of `ncols` columns of V (indices in colidx[]) against L = [L0 0; F G]:
+  // FWD: V <- L^-1 V, else V <- L^-T V.
+  //  * L0 lives in global memory as 32-row panels, k-major (pitch RBO_LP), 32x32 diagonal blocks pre-inverted, cut into
+  //    uniform 32-k chunks. Warp RBO_NCONS is the producer: it streams the chunks ONCE per pass into a 3-stage
+  //    shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), throttled by "empty" mbarriers.
+  //  * Each consumer warp owns 8 columns (a warp-task) for all 32 rows of a panel and accumulates with FP64 tensor-core
+  //    tiles (mma.sync m8n8k4): per chunk 8 B-fragment loads, 32 A-fragment loads, 32 DMMA; no cross-warp dependency
+  //    exists inside a solve because a column never leaves its warp.
+  //  * The fantasy rows (<= 8, per trajectory) are one more panel that already sits in shared memory.
   template <bool FWD>
   __device__ void tri_solve(int ncols, int nfan) {
     if (ncols <= 0) return;
-    const int RP = P.RP, N8 = P.N8, nb8 = P.nb8;
-    int KS = 1;
-    while (KS < 32 && ncols * (KS * 2) <= RBO_THREADS) KS *= 2;
-    const int ngroups = RBO_THREADS / KS, gid = tid / KS, part = tid & (KS - 1);
-    const int warp_first_gid = (tid & ~31) / KS;
-    for (int cb = 0; cb < ncols; cb += ngroups) {
-      if (cb + warp_first_gid >= ncols) continue;  // whole warp idle (warp-uniform)
-      const int ci = cb + gid;
-      const bool valid = ci < ncols;
-      double* vcol = V + colidx[valid ? ci : 0];
-      double acc[8], t[8];
-      if (FWD) {
-        for (int ib = 0; ib < nb8; ++ib) {
-          const double* pan = P.Lf + (size_t)32 * ib * (ib + 1);
-          const int nk = 8 * ib;
-#pragma unroll
-          for (int r = 0; r < 8; ++r) acc[r] = 0.0;
-          panel_rows<true>(pan, nk, part, KS, vcol, acc);
-          group_reduce(acc, KS);
-#pragma unroll
-          for (int r = 0; r < 8; ++r) t[r] = vcol[(size_t)(nk + r) * RP] - acc[r];
-          __syncwarp();
-          diag_apply<true>(pan + (size_t)nk * 8, t, part, KS, vcol + (size_t)nk * RP, valid, 8);
-          __syncwarp();
-        }
-        if (nfan > 0) {
-#pragma unroll
-          for (int r = 0; r < 8; ++r) acc[r] = 0.0;
-          panel_rows<false>(Fp, N8, part, KS, vcol, acc);
-          group_reduce(acc, KS);
-#pragma unroll
-          for (int r = 0; r < 8; ++r) t[r] = vcol[(size_t)(N8 + r) * RP] - acc[r];
-          __syncwarp();
-          diag_apply<false>(Fp + (size_t)N8 * 8, t, part, KS, vcol + (size_t)N8 * RP, valid, nfan);
-          __syncwarp();
-        }
-      } else {
-        if (nfan > 0) {
-          // w_bot = Ginv^T t restricted to the active rows: w_r = sum_{kk} Ginv[kk][r] t[kk], Ginv[kk][r] = Fp[(N8 + r)*8 + kk]
-#pragma unroll
-          for (int r = 0; r < 8; ++r) t[r] = (r < nfan) ? vcol[(size_t)(N8 + r) * RP] : 0.0;
-          __syncwarp();
-          double wb[8];
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            double s = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) s = fma(Fp[(size_t)(N8 + r) * 8 + kk], t[kk], s);
-            wb[r] = (r < nfan) ? s : 0.0;
+    const int RP = P.RP, N8 = P.N8, nb = P.nb32;
+    const int ntask = (ncols + 7) >> 3;  // a warp-task = 8 consecutive entries of colidx[]
+    const int nbatch = (ntask + RBO_NCONS - 1) / RBO_NCONS;
+    const unsigned chunks_per_pass = (unsigned)(nb * (nb + 1) / 2);
+    if (warp == RBO_NCONS) {
+      // ---------------- producer warp ----------------
+      if (lane == 0) {
+        unsigned q = qglob;
+        for (int bt = 0; bt < nbatch; ++bt)
+          for (int i = 0; i < nb; ++i) {
+            const int ib = FWD ? i : nb - 1 - i, nc = FWD ? ib + 1 : nb - ib;
+            const double* src = pan_ptr<FWD>(ib);
+            for (int c = 0; c < nc; ++c, ++q) {
+              if (q >= RBO_NSTAGE) empty_wait(q);
+              chunk_issue(q, src + (size_t)c * RBO_CHUNK_K * RBO_LP, RBO_CHUNK_K * RBO_LP);
+            }
           }
-          if (valid && part == 0) {
+      }
+      qglob += (unsigned)nbatch * chunks_per_pass;
+      __syncwarp();
+      return;
+    }
+    // ---------------- consumer warps ----------------
+    const int g = lane >> 2, tg = lane & 3;
+    unsigned q = qglob;
+    for (int bt = 0; bt < nbatch; ++bt) {
+      const int task = bt * RBO_NCONS + warp;
+      const bool wact = task < ntask;  // warp-uniform
+      // column offsets: cB for the B fragment (column g), c0/c1 for the C fragment (columns 2 tg, 2 tg + 1)
+      const int i0 = 8 * task;
+      const bool vB = wact && i0 + g < ncols, v0 = wact && i0 + 2 * tg < ncols, v1 = wact && i0 + 2 * tg + 1 < ncols;
+      const int first = colidx[wact ? i0 : 0];
+      const int cB = vB ? colidx[i0 + g] : first, c0 = v0 ? colidx[i0 + 2 * tg] : first, c1 = v1 ? colidx[i0 + 2 * tg + 1] : first;
+      // fantasy-row helpers: column fj = lane >> 2 (same as g), k-part fp = lane & 3
+      double* fv = V + cB;
+      const int fp = tg;
+
+      if (!FWD && nfan > 0 && wact) {
+        // w_bot = Ginv^T t restricted to the active rows: w_r = sum_kk Ginv[kk][r] t[kk], Ginv[kk][r] = Fp[(N8 + r)*8 + kk]
+        double t[8], wb[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) vcol[(size_t)(N8 + r) * RP] = wb[r];
-          }
-          // top rows: v_i -= sum_r F[r][i] w_bot[r]
-          for (int i = part; i < N8; i += KS) {
-            const double* f = Fp + (size_t)i * 8;
-            double s = 0.0;
+        for (int r = 0; r < 8; ++r) t[r] = (r < nfan) ? fv[(size_t)(N8 + r) * RP] : 0.0;
+        __syncwarp();
 #pragma unroll
-            for (int r = 0; r < 8; ++r) s = fma(f[r], wb[r], s);
-            if (valid) vcol[(size_t)i * RP] -= s;
-          }
-          __syncwarp();
+        for (int r = 0; r < 8; ++r) {
+          double s = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) s = fma(Fp[(size_t)(N8 + r) * 8 + kk], t[kk], s);
+          wb[r] = (r < nfan) ? s : 0.0;
         }
-        for (int ib = nb8 - 1; ib >= 0; --ib) {
-          const double* pan = P.Lb + ((size_t)8 * N8 * ib - (size_t)32 * ib * (ib - 1));
-          const int k0 = 8 * (ib + 1), nk = N8 - k0;
+        if (vB && fp == 0) {
 #pragma unroll
-          for (int r = 0; r < 8; ++r) acc[r] = 0.0;
-          panel_rows<true>(pan, nk, part, KS, vcol + (size_t)k0 * RP, acc);
-          group_reduce(acc, KS);
+          for (int r = 0; r < 8; ++r) fv[(size_t)(N8 + r) * RP] = wb[r];
+        }
+        for (int i = fp; i < N8; i += 4) {  // top rows: v_i -= sum_r F[r][i] w_bot[r]
+          const double* f = Fp + (size_t)i * 8;
+          double s = 0.0;
 #pragma unroll
-          for (int r = 0; r < 8; ++r) t[r] = vcol[(size_t)(8 * ib + r) * RP] - acc[r];
+          for (int r = 0; r < 8; ++r) s = fma(f[r], wb[r], s);
+          if (vB) fv[(size_t)i * RP] -= s;
+        }
+        __syncwarp();
+      }
+
+      double c[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) { c[mt][0] = 0.0; c[mt][1] = 0.0; }
+      for (int i = 0; i < nb; ++i) {
+        const int ib = FWD ? i : nb - 1 - i, nc = FWD ? ib + 1 : nb - ib, rb = RBO_BR * ib;
+        for (int cc = 0; cc < nc; ++cc, ++q) {
+          full_wait(q);
+          const double* buf = stage + (size_t)(q % RBO_NSTAGE) * RBO_CHUNK_K * RBO_LP;
+          if (wact) {
+            if (cc < nc - 1) {
+              const int krow0 = (FWD ? 0 : rb + RBO_BR) + cc * RBO_CHUNK_K;  // V row of the first k of this chunk
+              mma_chunk(buf, V + (size_t)krow0 * RP, cB, g, tg, c);
+            } else {
+              // last chunk of the panel = inverted diagonal block: t = b - acc (in place), then rows <- Dinv t
+#pragma unroll
+              for (int mt = 0; mt < 4; ++mt) {
+                const int row = rb + 8 * mt + g;
+                if (row < N8) {
+                  if (v0) V[(size_t)row * RP + c0] -= c[mt][0];
+                  if (v1) V[(size_t)row * RP + c1] -= c[mt][1];
+                }
+                c[mt][0] = 0.0; c[mt][1] = 0.0;
+              }
+              __syncwarp();
+              mma_chunk(buf, V + (size_t)rb * RP, cB, g, tg, c);
+              __syncwarp();
+#pragma unroll
+              for (int mt = 0; mt < 4; ++mt) {
+                const int row = rb + 8 * mt + g;
+                if (row < N8) {
+                  if (v0) V[(size_t)row * RP + c0] = c[mt][0];
+                  if (v1) V[(size_t)row * RP + c1] = c[mt][1];
+                }
+                c[mt][0] = 0.0; c[mt][1] = 0.0;
+              }
+              __syncwarp();
+            }
+          }
           __syncwarp();
-          diag_apply<true>(pan + (size_t)nk * 8, t, part, KS, vcol + (size_t)(8 * ib) * RP, valid, 8);
-          __syncwarp();
+          if (lane == 0) empty_arrive(q);
         }
       }
+
+      if (FWD && nfan > 0 && wact) {
+        double a8[8], t[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a8[r] = 0.0;
+        fan_rows(Fp, N8, fp, fv, a8);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          a8[r] += __shfl_xor_sync(FULL, a8[r], 1);
+          a8[r] += __shfl_xor_sync(FULL, a8[r], 2);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t[r] = fv[(size_t)(N8 + r) * RP] - a8[r];
+        __syncwarp();
+        // v_r = sum_kk Ginv[r][kk] t[kk] (Ginv stored k-major at Fp[(N8 + kk)*8 + r]); lane fp computes rows fp and fp + 4
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int r = fp + 4 * h2;
+          double s = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) s = fma(Fp[(size_t)(N8 + kk) * 8 + r], t[kk], s);
+          if (r >= nfan) s = 0.0;
+          if (vB) fv[(size_t)(N8 + r) * RP] = s;
+        }
+        __syncwarp();
+      }
     }
+    qglob = q;
   }
 
   // ------------------------------------------------------------------------------------------------
@@ -362,21 +482,21 @@ struct K {
   // Writes sdmu, sdsig (grad sigma), sga (grad alpha), sHt (-(H alpha + mu-sigma cross term)), sHref (H alpha as the
   // reference computes it, Q1) and sgh = [alpha, g_mu, g_sig, g_muth, g_sigth, sigma, mu, finite].
   // ------------------------------------------------------------------------------------------------
-  __device__ void assemble_warp(int sl, int aidx, int np, int npairs_pre, int npairs_post, int post_off, int RSpre, int RSpost, int RShess, double fstar) {
+  __device__ void assemble_warp(int sl, int aidx, int np, int nout_pre, int nout_post, int post_off, int RSpre, int RSpost, int RShess, double fstar) {
     const int d = P.d, dd = d * d, q1 = d + 1, T2 = d * (d + 1) / 2;
     const double* ppre = sm + pl.ppre; const double* ppost = sm + pl.ppost; const double* phess = sm + pl.phess;
     double* dmu = sm + pl.sdmu + sl * d; double* dsig = sm + pl.sdsig + sl * d; double* ga = sm + pl.sga + sl * d;
     double* Ht = sm + pl.sHt + sl * dd; double* Href = sm + pl.sHref + sl * dd; double* gh = sm + pl.sgh + sl * 8;
-    auto pre = [&](int e) { double s = 0.0; for (int r = 0; r < RSpre; ++r) s += ppre[(size_t)r * npairs_pre + aidx * q1 + e]; return s; };
-    auto post = [&](int e) { double s = 0.0; for (int r = 0; r < RSpost; ++r) s += ppost[(size_t)r * npairs_post + post_off + e]; return s; };
+    auto pre = [&](int e) { double s = 0.0; for (int r = 0; r < RSpre; ++r) s += ppre[(size_t)r * nout_pre + aidx * q1 + e]; return s; };
+    auto post = [&](int p, int q) { double s = 0.0; for (int r = 0; r < RSpost; ++r) s += ppost[(size_t)r * nout_post + post_off + p * q1 + q]; return s; };
     auto hes = [&](int which, int e) { double s = 0.0; for (int r = 0; r < RShess; ++r) s += phess[((size_t)(r * np + aidx) * 2 + which) * (T2 + 1) + e]; return s; };
     const double mu = pre(0);
-    const double var = P.k0 - post(0);  // rbs.jl:528 (kx.w == |L^-1 kx|^2)
+    const double var = P.k0 - post(0, 0);  // rbs.jl:528 (kx.w == |L^-1 kx|^2)
     const double sigma = sqrt(var), isg = 1.0 / sigma;
     const GPart g = rule_eval(P.rule_id, P.sigma_tol, mu, sigma, P.theta1, fstar);
     bool fin = isfinite(g.g);
     for (int p = lane; p < d; p += 32) {
-      double m = pre(1 + p), sg = -post(1 + p) * isg;  // rbs.jl:514, 529
+      double m = pre(1 + p), sg = -post(0, 1 + p) * isg;  // rbs.jl:514, 529
       double a = g.g_mu * m + g.g_sig * sg;            // rbs.jl:567
       dmu[p] = m; dsig[p] = sg; ga[p] = a;
       fin = fin && isfinite(a);
@@ -385,7 +505,7 @@ struct K {
     const double bC = hes(0, T2), bW = hes(1, T2);
     for (int e = lane; e < T2; e += 32) {
       const int pq = tbld[e], p = pq & 0xff, q = pq >> 8;
-      double gram = post(tri_idx(p + 1, q + 1, q1)), hc = hes(0, e), hw = hes(1, e);
+      double gram = post(p + 1, q + 1), hc = hes(0, e), hw = hes(1, e);
       if (p == q) { hc += bC; hw += bW; }
       double hs = (-dsig[p] * dsig[q] - gram - hw) * isg;                                                            // rbs.jl:541-546
       double href = g.g_mumu * dmu[p] * dmu[q] + g.g_mu * hc + g.g_sigsig * dsig[p] * dsig[q] + g.g_sig * hs;        // rbs.jl:568
@@ -552,7 +672,7 @@ struct K {
   // there, si[I_BEST] (or -1), si[I_EVALS]. Ties resolve to the lowest start index (findmin: first minimum).
   // ------------------------------------------------------------------------------------------------
   __device__ void multistart(size_t tape_off) {
-    const int d = P.d, W = P.W, q1 = d + 1, T = q1 * (q1 + 1) / 2;
+    const int d = P.d, W = P.W, q1 = d + 1;
     __syncthreads();
     if (tid == 0) {
       si[I_BEST] = -1; si[I_EVALS] = 0; misc[0] = 0.0;
@@ -562,41 +682,46 @@ struct K {
     }
     __syncthreads();
     int nact = si[I_NACT];
+    PT_DECL;
     while (nact > 0) {
       auto pt = [&](int s) { return (const double*)(sm + pl.sxt + alist[s] * d); };
       auto cb = [&](int s) { return alist[s] * P.CS; };
+      PT_MARK(9);
       fill_columns(nact, pt, cb);
-      for (int i = tid; i < nact * q1; i += RBO_THREADS) {
-        int s = i / q1, q = i - s * q1, col = alist[s] * P.CS + q;
-        colidx[i] = col;
-        pairs[i] = col | (CCOL << 16);  // mu = kx.c, grad mu = grad_kx c (rbs.jl:513-514)
-      }
+      for (int i = tid; i < nact * q1; i += RBO_THREADS) { int s = i / q1; colidx[i] = alist[s] * P.CS + (i - s * q1); }
+      for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS, q1, CCOL, 1, s * q1);  // mu = kx.c, grad mu = grad_kx c (rbs.jl:513-514)
       __syncthreads();
-      const int RSpre = choose_rs((nact * q1 + 71) / 72);
-      reduce_pairs(nact * q1, sm + pl.ppre, RSpre);
+      PT_MARK(0);
+      const int nbq = nblk16(q1);
+      const int RSpre = choose_rs(nact * nbq);
+      colprod(nact, nact * q1, sm + pl.ppre, RSpre);
       __syncthreads();  // the solve below overwrites the raw columns in place
+      PT_MARK(1);
       tri_solve<true>(nact * q1, nf);
-      for (int i = tid; i < nact * T; i += RBO_THREADS) {
-        int s = i / T, e = i - s * T, pq = tblq[e], col = alist[s] * P.CS;
-        pairs[i] = (col + (pq & 0xff)) | ((col + (pq >> 8)) << 16);  // |v0|^2, V_p.v0, V_p.V_q
-      }
+      for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS, q1, alist[s] * P.CS, q1, s * q1 * q1);  // |v0|^2, V_p.v0, V_p.V_q
       __syncthreads();
-      const int RSpost = choose_rs((nact * T + 71) / 72);
-      reduce_pairs(nact * T, sm + pl.ppost, RSpost);
+      PT_MARK(2);
+      const int RSpost = choose_rs(nact * nbq * nbq);
+      colprod(nact, nact * q1 * q1, sm + pl.ppost, RSpost);
       for (int i = tid; i < nact; i += RBO_THREADS) colidx[i] = alist[i] * P.CS;
       __syncthreads();
+      PT_MARK(3);
       tri_solve<false>(nact, nf);  // w = L^-T v0 (rbs.jl:525)
       __syncthreads();
-      const int RShess = choose_rs(nact * ((d * (d + 1) / 2 + 55) / 56));
-      reduce_hess(nact, pt, cb, cb, RShess);
+      PT_MARK(4);
+      const int nbd = nblk16(d);
+      const int RShess = choose_rs(nact * nbd * (nbd + 1) / 2);
+      hess_sums(nact, pt, cb, cb, RShess);
       __syncthreads();
+      PT_MARK(5);
       // per-start logic: one warp per active slot
       for (int s = warp; s < nact; s += RBO_NWARPS) {
         const int sl = alist[s];
-        assemble_warp(sl, s, nact, nact * q1, nact * T, s * T, RSpre, RSpost, RShess, misc[1]);
+        assemble_warp(sl, s, nact, nact * q1, nact * q1 * q1, s * q1 * q1, RSpre, RSpost, RShess, misc[1]);
         slot_logic_warp(sl);
       }
       __syncthreads();
+      PT_MARK(6);
       if (tid == 0) {
         int na2 = 0;
         for (int i = 0; i < nact; ++i) {
@@ -620,6 +745,10 @@ struct K {
         si[I_NACT] = na2;
       }
       __syncthreads();
+      PT_MARK(7);
+#ifdef RBO_PHASE_TIMERS
+      if (tid == 0) atomicAdd(&g_phase_cycles[15], 1ull);
+#endif
       nact = si[I_NACT];
     }
     if (tid == 0 && si[I_BEST] < 0) {
@@ -633,13 +762,17 @@ struct K {
 }  // namespace
 
 __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __grid_constant__ DevProblem P) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   K k(P, smem);
-  const int tid = k.tid, d = P.d, N8 = P.N8, NR = P.NR, RP = P.RP, h = P.h, q1 = d + 1, T = q1 * (q1 + 1) / 2;
+  const int tid = k.tid, d = P.d, N8 = P.N8, NR = P.NR, RP = P.RP, h = P.h, q1 = d + 1;
   double* bestx = k.bestx;
   double* misc = k.misc;  // misc[0] best f, misc[1] fstar, misc[2..7] scalars, misc[8..] scratch
   int* si = k.si;
   k.build_tables();
+  k.mbar_init();
+  for (int i = tid; i < NR * RP; i += RBO_THREADS) k.V[i] = 0.0;  // rows beyond the fantasy block are read (times exact zeros of L0's padding) but never written
+  if (P.xsm) for (int i = tid; i < d * N8; i += RBO_THREADS) k.Xs[(i / N8) * P.XP + (i % N8)] = __ldg(P.Xb + i);
+  __syncthreads();
 
   for (;;) {
     __syncthreads();
@@ -651,13 +784,12 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
     // ---- trajectory init: reset!(fs) (rbs.jl:476-480) ----
     for (int i = tid; i < (N8 + RBO_MAXFAN) * 8; i += RBO_THREADS) k.Fp[i] = 0.0;
     for (int i = tid; i < 64; i += RBO_THREADS) k.G[i] = ((i >> 3) == (i & 7)) ? 1.0 : 0.0;
-    for (int i = tid; i < (h + 2) * NR; i += RBO_THREADS) k.cs[i] = (i < N8) ? __ldg(P.c0 + i) : 0.0;
+    for (int i = tid; i < NR; i += RBO_THREADS) { double c = (i < N8) ? __ldg(P.c0 + i) : 0.0; k.cst[i] = c; k.V[(size_t)i * RP + k.CCOL] = c; }
     for (int i = tid; i < NR; i += RBO_THREADS) k.u[i] = (i < N8) ? __ldg(P.u0 + i) : 0.0;
     __syncthreads();
     if (tid < 8) k.Fp[(size_t)(N8 + tid) * 8 + tid] = 1.0;  // inverse of the identity fantasy block
     if (tid == 0) { misc[1] = P.ymin_base; si[I_TSTATUS] = RBO_TRAJ_OK; }
     k.nf = 0;
-    k.set_column(k.CCOL, k.cs);
     __syncthreads();
 
     if (P.flags & RBO_FLAG_MYOPIC_INTERNAL) {
@@ -694,34 +826,34 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
 
       // ============ joint draw at x_step (observables.jl:106-121, rbs.jl:588-611) and condition! (rbs.jl:431-441) ============
       {
+        PT_DECL;
         auto pt = [&](int) { return (const double*)bestx; };
         auto cb0 = [&](int) { return 0; };
         k.fill_columns(1, pt, cb0);
         k.set_column(k.UCOL, k.u);
-        for (int i = tid; i < q1; i += RBO_THREADS) { k.colidx[i] = i; k.pairs[i] = i | (k.CCOL << 16); }
+        for (int i = tid; i < q1; i += RBO_THREADS) k.colidx[i] = i;
+        if (tid == 0) k.set_item(0, 0, q1, k.CCOL, 1, 0);  // mu, grad mu
         __syncthreads();
-        const int RSpre = k.choose_rs(1);
-        k.reduce_pairs(q1, smem + k.pl.ppre, RSpre);  // mu, grad mu
+        const int nbq = K::nblk16(q1);
+        const int RSpre = k.choose_rs(nbq);
+        k.colprod(1, q1, smem + k.pl.ppre, RSpre);
         __syncthreads();
         k.tri_solve<true>(q1, k.nf);
-        for (int e = tid; e <= T; e += RBO_THREADS) {
-          if (e < T) { int pq = k.tblq[e]; k.pairs[e] = (pq & 0xff) | ((pq >> 8) << 16); }
-          else k.pairs[e] = 0 | (k.UCOL << 16);  // l . u
-        }
+        if (tid == 0) { k.set_item(0, 0, q1, 0, q1, 0); k.set_item(1, 0, 1, k.UCOL, 1, q1 * q1); }  // V'V and l . u
         __syncthreads();
-        const int RSpost = k.choose_rs((T + 1 + 71) / 72);
-        k.reduce_pairs(T + 1, smem + k.pl.ppost, RSpost);
+        const int nsg = q1 * q1 + 1;
+        const int RSpost = k.choose_rs(nbq * nbq + 1);
+        k.colprod(2, nsg, smem + k.pl.ppost, RSpost);
         __syncthreads();
         // Sigma = Dk(0) - A K^-1 A' = Dk(0) - V'V (rbs.jl:531-536)
         double* Sg = misc + 8;  // (d+1) x (d+1)
-        for (int e = tid; e <= T; e += RBO_THREADS) {
+        for (int e = tid; e < nsg; e += RBO_THREADS) {
           double acc = 0.0;
-          for (int r = 0; r < RSpost; ++r) acc += (smem + k.pl.ppost)[(size_t)r * (T + 1) + e];
-          if (e < T) {
-            const int pq = k.tblq[e], p = pq & 0xff, q = pq >> 8;
+          for (int r = 0; r < RSpost; ++r) acc += (smem + k.pl.ppost)[(size_t)r * nsg + e];
+          if (e < q1 * q1) {
+            const int p = e / q1, q = e - p * q1;
             const double dk = (p == q) ? (p == 0 ? P.k0 : -P.d2k0) : 0.0;  // eval_Dk(kernel, 0) rbf.jl:152-159
-            Sg[p * q1 + q] = dk - acc;
-            Sg[q * q1 + p] = dk - acc;
+            if (p <= q) { Sg[p * q1 + q] = dk - acc; Sg[q * q1 + p] = dk - acc; }  // Symmetric(...) takes the upper triangle
             if (e == 0) misc[4] = acc;  // |l|^2
           } else misc[5] = acc;         // l . u
         }
@@ -776,8 +908,9 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
         // coefficients: c = L^-T (L^-1 y) (rbs.jl:422-429); L^-1 y is maintained incrementally in u
         k.tri_solve<false>(1, k.nf);
         __syncthreads();
-        for (int j = tid; j < NR; j += RBO_THREADS) k.cs[(size_t)(step + 1) * NR + j] = k.V[(size_t)j * RP + k.CCOL];
+        for (int j = tid; j < NR; j += RBO_THREADS) k.cst[(size_t)(step + 1) * NR + j] = k.V[(size_t)j * RP + k.CCOL];
         __syncthreads();
+        PT_MARK(10);
       }
     }
 
@@ -800,6 +933,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
     __syncthreads();
 
     // ============ gradient(T) (rollout.jl:233-277) ============
+    PT_DECL;
     if (P.mode == RBO_MODE_VALUE_GRAD) {
       const int tc = si[I_CASE], t = si[I_T], nth = P.ntheta;
       if (tc == 1) {
@@ -815,12 +949,11 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
         __syncthreads();
         if (tid == 0) ybars[t + 1] = 1.0;  // rollout.jl:256
         const int CB_RAW = 0, CB_SOL = d + 3, CB_U = 2 * d + 4, CB_Q = 3 * d + 5;
-        const int nd = 2 * d + 1;
         const double* dd_m = P.dual_dirs ? P.dual_dirs + (size_t)m * h * d : nullptr;
         for (int i = t; i >= 1; --i) {
           // ---- re-evaluate policy solve i: fs(x_i, theta; fantasy_index = i-1) (rollout.jl:114-124) ----
           k.nf = i;
-          const double* c = k.cs + (size_t)i * NR;
+          const double* c = k.cst + (size_t)i * NR;
           const double* xi = k.Xf + (size_t)i * d;
           auto pt = [&](int) { return xi; };
           auto cbr = [&](int) { return CB_RAW; };
@@ -833,25 +966,28 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
             int j = idx / q1, q = idx - j * q1;
             k.V[(size_t)j * RP + CB_SOL + q] = k.V[(size_t)j * RP + CB_RAW + q];
           }
-          for (int q = tid; q < q1; q += RBO_THREADS) { k.colidx[q] = CB_SOL + q; k.pairs[q] = (CB_RAW + q) | (k.CCOL << 16); }
+          for (int q = tid; q < q1; q += RBO_THREADS) k.colidx[q] = CB_SOL + q;
+          if (tid == 0) k.set_item(0, CB_RAW, q1, k.CCOL, 1, 0);
           __syncthreads();
-          const int RSpre = k.choose_rs(1);
-          k.reduce_pairs(q1, smem + k.pl.ppre, RSpre);
+          const int nbq = K::nblk16(q1), nbd = K::nblk16(d);
+          const int RSpre = k.choose_rs(nbq);
+          k.colprod(1, q1, smem + k.pl.ppre, RSpre);
           k.tri_solve<true>(q1, k.nf);
-          for (int e = tid; e < T; e += RBO_THREADS) { int pq = k.tblq[e]; k.pairs[e] = (CB_SOL + (pq & 0xff)) | ((CB_SOL + (pq >> 8)) << 16); }
           __syncthreads();
-          const int RSpost = k.choose_rs((T + 71) / 72);
-          k.reduce_pairs(T, smem + k.pl.ppost, RSpost);
+          if (tid == 0) k.set_item(0, CB_SOL, q1, CB_SOL, q1, 0);
+          __syncthreads();
+          const int RSpost = k.choose_rs(nbq * nbq);
+          k.colprod(1, q1 * q1, smem + k.pl.ppost, RSpost);
           __syncthreads();
           k.tri_solve<false>(q1, k.nf);  // w = SOL[:,0], Dw = SOL[:,1..d] (rbs.jl:525-526)
           __syncthreads();
-          const int RShess = k.choose_rs((d * (d + 1) / 2 + 55) / 56);
-          k.reduce_hess(1, pt, cbr, cbs, RShess);
+          const int RShess = k.choose_rs(nbd * (nbd + 1) / 2);
+          k.hess_sums(1, pt, cbr, cbs, RShess);
           __syncthreads();
           if (k.warp == 0) {
             double fst = P.ymin_base;  // f* over the active slice y[1:N+i]
             for (int j = 0; j < i; ++j) fst = fmin(fst, k.yf[j]);
-            k.assemble_warp(0, 0, 1, q1, T, 0, RSpre, RSpost, RShess, fst);
+            k.assemble_warp(0, 0, 1, q1, q1 * q1, 0, RSpre, RSpost, RShess, fst);
             if (tid == 0) {
               misc[2] = fst;
               // ---- solve_dual_x for j = i (rollout.jl:150-191) with the contributions of later solves already pushed ----
@@ -898,7 +1034,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
               double psi, a_, b_, gb_;
               kern_radial(P.kern, rho2, psi, a_, b_, gb_);
               if (!(rho2 > 0.0)) b_ = 0.0;
-              double cp = c[rowp], rd = 0.0;
+              double cp = k.V[(size_t)rowp * RP + k.CCOL], rd = 0.0;
               for (int a = 0; a < d; ++a) {
                 double r = k.xcoord(j, a) - xp[a];
                 double uu = -b_ * r;
@@ -908,20 +1044,17 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
               double ud = -b_ * rd;
               rowU[d] = ud; rowQ[d] = ud * cp;
             }
-            for (int e = tid; e < 2 * q1; e += RBO_THREADS) {
-              int q = e >> 1;
-              k.pairs[e] = (CB_U + q) | (((e & 1) ? CB_SOL : k.CCOL) << 16);  // u.c (even) ; u.w (odd)
-            }
+            if (tid == 0) { k.set_item(0, CB_U, q1, k.CCOL, 1, 0); k.set_item(1, CB_U, q1, CB_SOL, 1, q1); }  // u.c ; u.w
             __syncthreads();
             // phase B: (dK c)_p = u.c ; u.w
-            const int RSb = k.choose_rs(1);
-            k.reduce_pairs(2 * q1, smem + k.pl.ppost, RSb);
+            const int RSb = k.choose_rs(2 * nbq);
+            k.colprod(2, 2 * q1, smem + k.pl.ppost, RSb);
             __syncthreads();
             double* uw = misc + 8;  // [q1]
             for (int e = tid; e < 2 * q1; e += RBO_THREADS) {
               double acc = 0.0;
               for (int r = 0; r < RSb; ++r) acc += (smem + k.pl.ppost)[(size_t)r * 2 * q1 + e];
-              if (e & 1) uw[e >> 1] = acc; else k.V[(size_t)rowp * RP + CB_Q + (e >> 1)] = acc;
+              if (e >= q1) uw[e - q1] = acc; else k.V[(size_t)rowp * RP + CB_Q + e] = acc;
             }
             for (int q = tid; q < q1; q += RBO_THREADS) k.colidx[q] = CB_Q + q;
             __syncthreads();
@@ -929,24 +1062,20 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
             k.tri_solve<true>(q1, k.nf);
             __syncthreads();
             k.tri_solve<false>(q1, k.nf);
-            for (int e = tid; e < q1 * nd; e += RBO_THREADS) {
-              int q = e / nd, w = e - q * nd;
-              int c1 = (w <= d) ? CB_RAW + w : CB_SOL + (w - d);  // w in [0,d]: raw kx / grad_kx ; w in (d, 2d]: Dw column
-              int c2 = (w <= d) ? CB_Q + q : CB_U + q;
-              k.pairs[e] = c1 | (c2 << 16);
-            }
+            // phase D: dots [kx, grad_kx]'.Q (w = 0..d) and Dw'.U (w = d+1..2d) per direction q
+            if (tid == 0) { k.set_item(0, CB_RAW, q1, CB_Q, q1, 0); k.set_item(1, CB_SOL + 1, d, CB_U, q1, q1 * q1); }
             __syncthreads();
-            // phase D: dots kx.Q, grad_kx.Q, Dw'U per direction
-            const int RSd = k.choose_rs((q1 * nd + 71) / 72);
-            k.reduce_pairs(q1 * nd, smem + k.pl.ppost, RSd);
+            const int nD = q1 * q1 + d * q1;
+            const int RSd = k.choose_rs(nbq * nbq + nbd * nbq);
+            k.colprod(2, nD, smem + k.pl.ppost, RSd);
             __syncthreads();
             // phase E: assemble delta grad alpha per direction and push it into the earlier duals
             if (tid < q1) {
               const int q = tid;
               const double* gh = smem + k.pl.sgh; const double* dmu = smem + k.pl.sdmu; const double* dsg = smem + k.pl.sdsig;
               const double* rowp_v = k.V + (size_t)rowp * RP;
-              auto dq = [&](int w) { double acc = 0.0; for (int r = 0; r < RSd; ++r) acc += (smem + k.pl.ppost)[(size_t)r * q1 * nd + q * nd + w]; return acc; };
-              const double cp = c[rowp], wp = rowp_v[CB_SOL];
+              auto dq = [&](int w) { double acc = 0.0; for (int r = 0; r < RSd; ++r) acc += (smem + k.pl.ppost)[(size_t)r * nD + w * q1 + q]; return acc; };
+              const double cp = rowp_v[k.CCOL], wp = rowp_v[CB_SOL];
               double dxv[RBO_MAXD];
               for (int a = 0; a < d; ++a) dxv[a] = (q < d) ? (a == q ? 1.0 : 0.0) : (dd_m ? dd_m[(size_t)p * d + a] : 0.0);
               // dkx_p = grad_k(x - X_p).(-dx) (rbf.jl:230-245); dgkx_p = Hk(x - X_p)(-dx) (rbf.jl:247-262)
@@ -986,11 +1115,11 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
           auto cb0 = [&](int) { return 0; };
           __syncthreads();
           k.fill_columns(1, pt, cb0);
-          k.set_column(k.CCOL, k.cs);
-          for (int q = tid; q < q1; q += RBO_THREADS) k.pairs[q] = q | (k.CCOL << 16);
+          k.set_column(k.CCOL, k.cst);
+          if (tid == 0) k.set_item(0, 0, q1, k.CCOL, 1, 0);
           __syncthreads();
-          const int RSpre = k.choose_rs(1);
-          k.reduce_pairs(q1, smem + k.pl.ppre, RSpre);
+          const int RSpre = k.choose_rs(K::nblk16(q1));
+          k.colprod(1, q1, smem + k.pl.ppre, RSpre);
           __syncthreads();
           for (int a = tid; a < d; a += RBO_THREADS) {
             double dmu = 0.0;
@@ -1003,6 +1132,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
       }
     }
     __syncthreads();
+    PT_MARK(11);
     if (tid == 0 && P.status) P.status[m] = si[I_TSTATUS];
   }
 }
@@ -1134,3 +1264,13 @@ __global__ void rbo_fp64_peak_kernel(double* out, int iters) {
 }
 
 }  // namespace rbo
+
+#ifdef RBO_PHASE_TIMERS
+// development aid (not part of include/rbo.h): per-phase cycle counters of the rollout kernel
+extern "C" int rbo_debug_phase_cycles(void*, unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, rbo::g_phase_cycles, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(rbo::g_phase_cycles, z, sizeof(z)); }
+  return 0;
+}
+#endif

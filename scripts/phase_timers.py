@@ -1,0 +1,38 @@
+"""Per-phase cycle breakdown of the rollout kernel (needs csrc/librbo_timers.so built with -DRBO_PHASE_TIMERS)."""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ["RBO_LIB_PATH"] = os.path.join(ROOT, "rollout-bayesian-optimization_b200", "csrc", "librbo_timers.so")
+sys.path.insert(0, ROOT)
+import numpy as np
+import __graft_entry__ as g
+
+NAMES = ["fill_columns", "reduce_pre", "fwd_solve", "reduce_post", "bwd_solve", "reduce_hess", "slot_logic", "bookkeeping",
+         "ts:sync", "round_gap", "draw+condition", "adjoint", "ts:issue", "ts:wait", "ts:compute(w0)", "rounds"]
+
+def main(name="C3", M=296):
+    pkg = g.load_package()
+    wl = pkg.problems.make_workload(name, M=M)
+    sur = wl.surrogate()
+    eng = pkg.RolloutEngine(0)
+    eng.set_surrogate(pkg.FantasySurrogate(sur, wl.h))
+    eng.generate_normals(M, wl.h + 1)
+    eng.set_starts(pkg.generate_initial_guesses(wl.S, wl.lbs, wl.ubs))
+    dd = np.asfortranarray(np.random.default_rng(7).random((wl.d, wl.h, M)))
+    vals, gx, gt = np.zeros(M), np.zeros((wl.d, M), order="F"), np.zeros((1, M), order="F")
+    out = (ctypes.c_ulonglong * 16)()
+    fn = eng.lib.rbo_debug_phase_cycles
+    fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+    s = eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), vals, gx, gt, dual_dirs=dd)
+    fn(eng.handle.h, out, 1)
+    s = eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), vals, gx, gt, dual_dirs=dd)
+    fn(eng.handle.h, out, 1)
+    tot = sum(out[i] for i in range(12))
+    rounds = out[15]
+    print(f"{name} M={M}: kernel_ms={s.kernel_ms:.2f} traj/s={M / s.kernel_ms * 1e3:.1f} rounds/traj={rounds / M:.1f} evals/traj={s.n_evals / M:.1f} cycles/traj={tot / M:.3e}")
+    for i in range(15):
+        if NAMES[i] != "-":
+            print(f"  {NAMES[i]:<16} {100 * out[i] / tot:5.1f}%   {out[i] / max(rounds, 1):9.0f} cycles/round")
+    eng.close()
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "C3", int(sys.argv[2]) if len(sys.argv) > 2 else 296)
