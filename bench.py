@@ -134,7 +134,7 @@ def run_reference(args):
     pkg = graft.load_package()
     wl_full = pkg.problems.make_workload(args.workload, M=args.M)
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or max(cores * 4, 32)
+    sample = args.cpu_sample or max(cores * 48, 256)
     times = []
     for i in range(args.warmup + args.steps):
         tput, dt, _ = cpu_baseline(args.workload, sample, cores, args.normals)
@@ -290,7 +290,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world >= 1:
             cores = os.cpu_count() or 1
-            sample = args.cpu_sample or max(cores * 4, 32)
+            sample = args.cpu_sample or max(cores * 48, 256)
             tput, dt, r = cpu_baseline(args.workload, sample, cores, args.normals)
             cpu = {"value": tput, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{sample} of {M} trajectories in {dt:.1f} s (oracle/rbo_oracle.cpp = C++/OpenMP restatement of the reference; Julia not installed)"}

@@ -332,18 +332,27 @@ struct PlanChoice { int W, RP, NR, RSmax, NPmax, xsm; size_t bytes; };
 static bool choose_plan(const rbo_handle* h, int hor, int S, PlanChoice* pc) {
   const int d = h->d, N8 = h->N8, CS = d + 3, NR = std::max(N8 + RBO_MAXFAN, h->nb32 * RBO_BR);
   const int nadj = ncols_adjoint(d);
-  for (int W = std::min(S, RBO_NWARPS); W >= 1; --W) {
-    // prefer a W that divides the start list into equal passes (fewer idle slots at the tail)
+  // Preference: (i) row splits >= 2 and the base locations in shared memory, with the largest W that still allows it
+  // (provided that W covers at least half of the start list); (ii) otherwise the largest W with whatever fits.
+  auto try_plan = [&](int W, int RSmax, int xsm) {
     int RP = std::max(W * CS, nadj) + 2;
     if ((RP & 1) == 0) RP += 1;  // odd pitch: conflict-free column walks
-    // preference order: keep the base locations in shared memory, then more row splits
+    int NPmax = npairs_max(d, W);
+    SmemPlan pl = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm);
+    size_t bytes = (size_t)pl.total * 8;
+    if (bytes > (size_t)h->max_smem) return false;
+    *pc = {W, RP, NR, RSmax, NPmax, xsm, bytes};
+    return true;
+  };
+  const int Wmax = std::min(S, RBO_NCONS);
+  for (int W = Wmax; W >= std::max(1, std::min(Wmax, (S + 1) / 2)); --W) {
+    int rs = std::min(4, std::max(2, RBO_NWARPS / W));
+    if (try_plan(W, rs, 1)) return true;
+    if (rs > 2 && try_plan(W, 2, 1)) return true;
+  }
+  for (int W = Wmax; W >= 1; --W) {
     const int tries[4][2] = {{2, 1}, {1, 1}, {2, 0}, {1, 0}};
-    for (auto& t : tries) {
-      int NPmax = npairs_max(d, W);
-      SmemPlan pl = make_plan(d, N8, hor, W, RP, NR, t[0], NPmax, t[1]);
-      size_t bytes = (size_t)pl.total * 8;
-      if (bytes <= (size_t)h->max_smem) { *pc = {W, RP, NR, t[0], NPmax, t[1], bytes}; return true; }
-    }
+    for (auto& t : tries) if (try_plan(W, t[0], t[1])) return true;
   }
   return false;
 }

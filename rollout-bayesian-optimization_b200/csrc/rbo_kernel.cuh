@@ -85,7 +85,7 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.Xs = take(xsm ? d * (N8 + 1) : 0);
   p.stage = take(RBO_NSTAGE * RBO_CHUNK_K * RBO_LP);
   p.mbar = take(2 * RBO_NSTAGE + 2);
-  p.sx = take(W * d); p.sxt = take(W * d); p.sg = take(W * d); p.sH = take(W * dd); p.sA = take(W * dd); p.sp = take(W * d);
+  p.sx = take(W * d); p.sxt = take(W * d); p.sg = take(W * d); p.sH = take(W * dd); p.sA = take(W * dd); p.sp = take(2);
   p.sHt = take(W * dd); p.sHref = take(W * dd); p.sga = take(W * d); p.sdmu = take(W * d); p.sdsig = take(W * d); p.sgh = take(W * 8);
   p.sf = take(W); p.slam = take(W); p.spred = take(W); p.shs = take(W);
   p.ppre = take(RSmax * W * q1);

@@ -164,15 +164,20 @@ struct K {
       const int ca0 = colA + min(16 * mb + g, na - 1), ca1 = colA + min(16 * mb + 8 + g, na - 1);
       const int cb0 = colB + min(16 * nk + g, nb - 1), cb1 = colB + min(16 * nk + 8 + g, nb - 1);
       double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+      const bool hiA = na - 16 * mb > 8, hiB = nb - 16 * nk > 8;  // second 8-row / 8-column tile in use (warp-uniform)
+#pragma unroll 2
       for (int j0 = 4 * rs; j0 < nrows; j0 += 4 * RS) {
         const int j = j0 + tg;
         const bool in = j < nrows;
         const double* row = V + (size_t)(in ? j : 0) * RP;
-        const double a0 = in ? row[ca0] : 0.0, a1 = in ? row[ca1] : 0.0, b0 = in ? row[cb0] : 0.0, b1 = in ? row[cb1] : 0.0;
+        const double a0 = in ? row[ca0] : 0.0, b0 = in ? row[cb0] : 0.0;
         dmma(c00[0], c00[1], a0, b0);
-        dmma(c01[0], c01[1], a0, b1);
-        dmma(c10[0], c10[1], a1, b0);
-        dmma(c11[0], c11[1], a1, b1);
+        if (hiB) { const double b1 = in ? row[cb1] : 0.0; dmma(c01[0], c01[1], a0, b1); }
+        if (hiA) {
+          const double a1 = in ? row[ca1] : 0.0;
+          dmma(c10[0], c10[1], a1, b0);
+          if (hiB) { const double b1 = in ? row[cb1] : 0.0; dmma(c11[0], c11[1], a1, b1); }
+        }
       }
       double* o = dst + (size_t)rs * nout + it[4];
       const int p0 = 16 * mb + g, p1 = p0 + 8, q0 = 16 * nk + 2 * tg, q1_ = q0 + 8;
@@ -206,6 +211,7 @@ struct K {
       double cC[4][2], cW[4][2], bC = 0.0, bW = 0.0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) { cC[i][0] = cC[i][1] = 0.0; cW[i][0] = cW[i][1] = 0.0; }
+#pragma unroll 2
       for (int j0 = 4 * rs; j0 < nrows; j0 += 4 * RS) {
         const int j = j0 + tg;
         const bool in = j < nrows;
@@ -290,21 +296,24 @@ struct K {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
   }
 
-  // One 32-k chunk of a 32-row panel against 8 columns owned by this warp: C[4 row tiles][8x8] += L[32 x 32k] * V[32k x 8].
-  // buf: staged chunk, k-major with pitch RBO_LP; vrow0: V row of chunk-relative k = 0; cB: this lane's B-fragment column offset.
-  __device__ __forceinline__ void mma_chunk(const double* buf, const double* vrow0, int cB, int g, int tg, double c[4][2]) const {
+  // One 32-k chunk of a 32-row panel against the 8 columns of this warp's group: C[MTW row tiles][8x8] += L[rows x 32k] * V[32k x 8].
+  // buf: staged chunk, k-major with pitch RBO_LP, already offset to the warp's first row tile; vrow0: V row of chunk-relative
+  // k = 0; cB: this lane's B-fragment column offset.
+  template <int MTW>
+  __device__ __forceinline__ void mma_chunk(const double* buf, const double* vrow0, int cB, int g, int tg, double (*c)[2]) const {
     const int RP = P.RP;
     const double* vp = vrow0 + (size_t)tg * RP + cB;
     const double* ap = buf + (size_t)tg * RBO_LP + g;
 #pragma unroll
     for (int kt = 0; kt < RBO_CHUNK_K / 4; ++kt) {
       const double b = vp[(size_t)(4 * kt) * RP];
-      const double a0 = ap[4 * kt * RBO_LP], a1 = ap[4 * kt * RBO_LP + 8], a2 = ap[4 * kt * RBO_LP + 16], a3 = ap[4 * kt * RBO_LP + 24];
-      dmma(c[0][0], c[0][1], a0, b);
-      dmma(c[1][0], c[1][1], a1, b);
-      dmma(c[2][0], c[2][1], a2, b);
-      dmma(c[3][0], c[3][1], a3, b);
+#pragma unroll
+      for (int mt = 0; mt < MTW; ++mt) dmma(c[mt][0], c[mt][1], ap[4 * kt * RBO_LP + 8 * mt], b);
     }
+  }
+  __device__ __forceinline__ void group_sync(int NRQ, int group) const {  // the NRQ warps that share a column group
+    if (NRQ == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * NRQ) : "memory");
   }
 
   // ---- 8-row fantasy panel (shared memory, pitch 8): 4 lanes own one column and split k ----
@@ -340,9 +349,20 @@ struct K {
   template <bool FWD>
   __device__ void tri_solve(int ncols, int nfan) {
     if (ncols <= 0) return;
+    const int ngroups = (ncols + 7) >> 3;  // a column group = 8 consecutive entries of colidx[]
+    if (ngroups * 4 <= RBO_NCONS) tri_solve_impl<FWD, 4>(ncols, nfan);
+    else if (ngroups * 2 <= RBO_NCONS) tri_solve_impl<FWD, 2>(ncols, nfan);
+    else tri_solve_impl<FWD, 1>(ncols, nfan);
+  }
+
+  // NRQ warps share one column group: each owns 32 / NRQ rows (MTW = 4 / NRQ row tiles) of every panel and they meet at a
+  // named barrier around the diagonal step.
+  template <bool FWD, int NRQ>
+  __device__ void tri_solve_impl(int ncols, int nfan) {
+    constexpr int MTW = 4 / NRQ, GPB = RBO_NCONS / NRQ;  // row tiles per warp; column groups per batch
     const int RP = P.RP, N8 = P.N8, nb = P.nb32;
-    const int ntask = (ncols + 7) >> 3;  // a warp-task = 8 consecutive entries of colidx[]
-    const int nbatch = (ntask + RBO_NCONS - 1) / RBO_NCONS;
+    const int ngroups = (ncols + 7) >> 3;
+    const int nbatch = (ngroups + GPB - 1) / GPB;
     const unsigned chunks_per_pass = (unsigned)(nb * (nb + 1) / 2);
     if (warp == RBO_NCONS) {
       // ---------------- producer warp ----------------
@@ -364,82 +384,86 @@ struct K {
     }
     // ---------------- consumer warps ----------------
     const int g = lane >> 2, tg = lane & 3;
+    const int gl = warp / NRQ, rq = warp - gl * NRQ;  // group slot within the batch, row quarter
     unsigned q = qglob;
     for (int bt = 0; bt < nbatch; ++bt) {
-      const int task = bt * RBO_NCONS + warp;
-      const bool wact = task < ntask;  // warp-uniform
+      const int group = bt * GPB + gl;
+      const bool wact = gl < GPB && group < ngroups;  // warp-uniform
       // column offsets: cB for the B fragment (column g), c0/c1 for the C fragment (columns 2 tg, 2 tg + 1)
-      const int i0 = 8 * task;
+      const int i0 = 8 * group;
       const bool vB = wact && i0 + g < ncols, v0 = wact && i0 + 2 * tg < ncols, v1 = wact && i0 + 2 * tg + 1 < ncols;
       const int first = colidx[wact ? i0 : 0];
       const int cB = vB ? colidx[i0 + g] : first, c0 = v0 ? colidx[i0 + 2 * tg] : first, c1 = v1 ? colidx[i0 + 2 * tg + 1] : first;
-      // fantasy-row helpers: column fj = lane >> 2 (same as g), k-part fp = lane & 3
+      // fantasy-row helpers (done by the rq == 0 warp of the group): column = g, k-part fp = tg
       double* fv = V + cB;
       const int fp = tg;
 
       if (!FWD && nfan > 0 && wact) {
-        // w_bot = Ginv^T t restricted to the active rows: w_r = sum_kk Ginv[kk][r] t[kk], Ginv[kk][r] = Fp[(N8 + r)*8 + kk]
-        double t[8], wb[8];
+        if (rq == 0) {
+          // w_bot = Ginv^T t restricted to the active rows: w_r = sum_kk Ginv[kk][r] t[kk], Ginv[kk][r] = Fp[(N8 + r)*8 + kk]
+          double t[8], wb[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) t[r] = (r < nfan) ? fv[(size_t)(N8 + r) * RP] : 0.0;
-        __syncwarp();
+          for (int r = 0; r < 8; ++r) t[r] = (r < nfan) ? fv[(size_t)(N8 + r) * RP] : 0.0;
+          __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          double s = 0.0;
+          for (int r = 0; r < 8; ++r) {
+            double s = 0.0;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) s = fma(Fp[(size_t)(N8 + r) * 8 + kk], t[kk], s);
-          wb[r] = (r < nfan) ? s : 0.0;
+            for (int kk = 0; kk < 8; ++kk) s = fma(Fp[(size_t)(N8 + r) * 8 + kk], t[kk], s);
+            wb[r] = (r < nfan) ? s : 0.0;
+          }
+          if (vB && fp == 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) fv[(size_t)(N8 + r) * RP] = wb[r];
+          }
+          for (int i = fp; i < N8; i += 4) {  // top rows: v_i -= sum_r F[r][i] w_bot[r]
+            const double* f = Fp + (size_t)i * 8;
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) s = fma(f[r], wb[r], s);
+            if (vB) fv[(size_t)i * RP] -= s;
+          }
         }
-        if (vB && fp == 0) {
-#pragma unroll
-          for (int r = 0; r < 8; ++r) fv[(size_t)(N8 + r) * RP] = wb[r];
-        }
-        for (int i = fp; i < N8; i += 4) {  // top rows: v_i -= sum_r F[r][i] w_bot[r]
-          const double* f = Fp + (size_t)i * 8;
-          double s = 0.0;
-#pragma unroll
-          for (int r = 0; r < 8; ++r) s = fma(f[r], wb[r], s);
-          if (vB) fv[(size_t)i * RP] -= s;
-        }
-        __syncwarp();
+        group_sync(NRQ, gl);
       }
 
-      double c[4][2];
+      double c[MTW][2];
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) { c[mt][0] = 0.0; c[mt][1] = 0.0; }
+      for (int mt = 0; mt < MTW; ++mt) { c[mt][0] = 0.0; c[mt][1] = 0.0; }
+      const int rofs = 8 * MTW * rq;  // first row (within a panel) owned by this warp
       for (int i = 0; i < nb; ++i) {
         const int ib = FWD ? i : nb - 1 - i, nc = FWD ? ib + 1 : nb - ib, rb = RBO_BR * ib;
         for (int cc = 0; cc < nc; ++cc, ++q) {
           full_wait(q);
-          const double* buf = stage + (size_t)(q % RBO_NSTAGE) * RBO_CHUNK_K * RBO_LP;
+          const double* buf = stage + (size_t)(q % RBO_NSTAGE) * RBO_CHUNK_K * RBO_LP + rofs;
           if (wact) {
             if (cc < nc - 1) {
               const int krow0 = (FWD ? 0 : rb + RBO_BR) + cc * RBO_CHUNK_K;  // V row of the first k of this chunk
-              mma_chunk(buf, V + (size_t)krow0 * RP, cB, g, tg, c);
+              mma_chunk<MTW>(buf, V + (size_t)krow0 * RP, cB, g, tg, c);
             } else {
               // last chunk of the panel = inverted diagonal block: t = b - acc (in place), then rows <- Dinv t
 #pragma unroll
-              for (int mt = 0; mt < 4; ++mt) {
-                const int row = rb + 8 * mt + g;
+              for (int mt = 0; mt < MTW; ++mt) {
+                const int row = rb + rofs + 8 * mt + g;
                 if (row < N8) {
                   if (v0) V[(size_t)row * RP + c0] -= c[mt][0];
                   if (v1) V[(size_t)row * RP + c1] -= c[mt][1];
                 }
                 c[mt][0] = 0.0; c[mt][1] = 0.0;
               }
-              __syncwarp();
-              mma_chunk(buf, V + (size_t)rb * RP, cB, g, tg, c);
-              __syncwarp();
+              group_sync(NRQ, gl);  // every t row of the panel is in place
+              mma_chunk<MTW>(buf, V + (size_t)rb * RP, cB, g, tg, c);
+              group_sync(NRQ, gl);  // every warp of the group has read t
 #pragma unroll
-              for (int mt = 0; mt < 4; ++mt) {
-                const int row = rb + 8 * mt + g;
+              for (int mt = 0; mt < MTW; ++mt) {
+                const int row = rb + rofs + 8 * mt + g;
                 if (row < N8) {
                   if (v0) V[(size_t)row * RP + c0] = c[mt][0];
                   if (v1) V[(size_t)row * RP + c1] = c[mt][1];
                 }
                 c[mt][0] = 0.0; c[mt][1] = 0.0;
               }
-              __syncwarp();
+              group_sync(NRQ, gl);  // solved rows visible to the group before they feed later panels
             }
           }
           __syncwarp();
@@ -447,7 +471,7 @@ struct K {
         }
       }
 
-      if (FWD && nfan > 0 && wact) {
+      if (FWD && nfan > 0 && wact && rq == 0) {
         double a8[8], t[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) a8[r] = 0.0;
@@ -522,7 +546,8 @@ struct K {
     __syncwarp();
   }
 
-  // Cholesky of the n x n row-major matrix A (n <= 32) by one warp; lane i owns row i. Returns false if not PD.
+  // Cholesky of the n x n row-major matrix A (n <= 32) by one warp; lane i owns row i; the diagonal of the result holds
+  // 1 / l_jj. Returns false if not PD.
   __device__ bool chol_warp(double* A, int n) const {
     for (int j = 0; j < n; ++j) {
       double t = 0.0;
@@ -532,9 +557,9 @@ struct K {
       }
       const double tj = __shfl_sync(FULL, t, j);
       if (!(tj > 0.0) || !isfinite(tj)) return false;
-      const double ljj = sqrt(tj);
-      if (lane == j) A[j * n + j] = ljj;
-      else if (lane > j && lane < n) A[lane * n + j] = t / ljj;
+      const double inv = rsqrt(tj);  // the diagonal stores 1 / l_jj: the substitutions multiply instead of dividing
+      if (lane == j) A[j * n + j] = inv;
+      else if (lane > j && lane < n) A[lane * n + j] = t * inv;
       __syncwarp();
     }
     return true;
@@ -628,12 +653,12 @@ struct K {
       // solve (H_FF + lam I) p = -g_F : forward then backward substitution, lane i holds component i
       double t = lane < nfree ? -g[myc] : 0.0;
       for (int i = 0; i < nfree; ++i) {
-        const double pi = __shfl_sync(FULL, t, i) / A[i * nfree + i];
+        const double pi = __shfl_sync(FULL, t, i) * A[i * nfree + i];
         if (lane == i) t = pi;
         else if (lane > i && lane < nfree) t = fma(-A[lane * nfree + i], pi, t);
       }
       for (int i = nfree - 1; i >= 0; --i) {
-        const double pi = __shfl_sync(FULL, t, i) / A[i * nfree + i];
+        const double pi = __shfl_sync(FULL, t, i) * A[i * nfree + i];
         if (lane == i) t = pi;
         else if (lane < i) t = fma(-A[i * nfree + lane], pi, t);
       }
