@@ -281,6 +281,14 @@ def main():
     e2e_ms = timed(e2e_step, e2e_steps, 1) / e2e_steps
     e2e_value = M / (e2e_ms * 1e-3)
     ok_e2e = int(st_pin.max()) == 0
+    # host wall-clock breakdown of one more e2e step (not part of any reported number)
+    brk = {}
+    def _t(name, fn):
+        t0 = time.perf_counter(); fn(); torch.cuda.synchronize(dev); brk[name] = round(1e3 * (time.perf_counter() - t0), 3)
+    _t("set_surrogate", lambda: eng.set_surrogate(fs))
+    _t("set_normals", lambda: eng.set_normals(rn_pin))
+    _t("set_starts", lambda: eng.set_starts(starts_pin))
+    _t("rollout+d2h", lambda: eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, h, fmini, res_pin, gx_pin, gt_pin, dual_dirs=dd_pin, status=st_pin))
 
     if rank == 0:
         peak_tf = eng.fp64_peak()
@@ -300,7 +308,7 @@ def main():
             "data": "synthetic", "config": workload_config(wl, args.normals, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
-                    "steps": e2e_steps, "all_trajectories_ok": ok_e2e},
+                    "steps": e2e_steps, "all_trajectories_ok": ok_e2e, "host_breakdown_ms": brk},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved_per_gpu, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_per_gpu / peak_tf,
                          "traffic": None,

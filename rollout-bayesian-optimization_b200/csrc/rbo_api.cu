@@ -390,7 +390,7 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   P.d = h->d; P.N = h->N; P.N8 = h->N8; P.nb8 = h->nb8; P.nb32 = h->nb32; P.h = horizon; P.S = S; P.W = pc.W; P.RSmax = pc.RSmax; P.NPmax = pc.NPmax; P.xsm = pc.xsm; P.XP = h->N8 + 1;
   P.CS = h->d + 3; P.RP = pc.RP; P.NR = pc.NR; P.M = M; P.hp1 = h->hp1; P.mode = mode; P.flags = flags; P.ntheta = ntheta;
   P.kern = h->kern; P.rule_id = h->rule_id; P.sigma_tol = h->sigma_tol; P.sigma_n2 = h->sigma_n2; P.k0 = h->k0; P.d2k0 = h->d2k0;
-  P.ymin_base = h->ymin_base; P.fmini = fmini; P.theta1 = theta[0]; P.htol = h->htol; P.so = h->so;
+  P.ymin_base = h->ymin_base; P.m52_c = std::sqrt(5.0) / h->kern.th[0]; P.fmini = fmini; P.theta1 = theta[0]; P.htol = h->htol; P.so = h->so;
   for (int a = 0; a < h->d; ++a) { P.x0[a] = x0[a]; P.lbs[a] = lbs[a]; P.ubs[a] = ubs[a]; }
   P.Xb = h->Xb; P.yb = h->yb; P.c0 = h->c0; P.u0 = h->u0; P.Lf = h->Lf; P.Lb = h->Lb; P.rn = h->rn; P.starts = h->starts;
   P.dual_dirs = dual_dirs_dev; P.x_forced = x_forced_dev;

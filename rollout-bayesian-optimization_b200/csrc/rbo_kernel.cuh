@@ -20,6 +20,7 @@ struct DevProblem {
   KernelSpec kern;
   int rule_id;
   double sigma_tol, sigma_n2, k0, d2k0, ymin_base;
+  double m52_c;           // sqrt(5) / length-scale (Matern-5/2 fast path)
   double fmini, theta1, htol;
   rbo_solver_opts so;
   double x0[RBO_MAXD], lbs[RBO_MAXD], ubs[RBO_MAXD];
@@ -58,7 +59,7 @@ struct SmemPlan {
   int sx, sxt, sg, sH, sA, sp;               // per slot: x, trial x, gradient, Hessian, Cholesky scratch, step
   int sHt, sHref, sga, sdmu, sdsig, sgh;     // per slot: trial Hessian (-H alpha), reference H alpha, grad alpha, grad mu, grad sigma, scalars
   int sf, slam, spred, shs;                  // per slot scalars
-  int ppre, ppost, phess;                    // partial sums of the row reductions
+  int ppre, ppost, ppost1, phess;            // partial sums of the row reductions
   int bestx, misc, adj;                      // [d] best candidate ; scalar/scratch area ; adjoint duals
   int pairs, tbl, ints;                      // int areas (in doubles)
   int total;                                 // total doubles
@@ -90,6 +91,7 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.sf = take(W); p.slam = take(W); p.spred = take(W); p.shs = take(W);
   p.ppre = take(RSmax * W * q1);
   p.ppost = take(RSmax * NPmax);
+  p.ppost1 = take(RSmax * W * q1);
   p.phess = take(RSmax * W * 2 * (T2 + 1));
   p.bestx = take(d);
   p.misc = take(64 + 2 * q1 * q1);

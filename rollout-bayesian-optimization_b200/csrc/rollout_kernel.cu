@@ -17,6 +17,10 @@
 //     perturbation columns (rbs.jl:633-764) are pushed into the right-hand sides of the earlier duals.
 #include "rbo_kernel.cuh"
 
+#ifndef RBO_OVERLAP
+#define RBO_OVERLAP 0  // 1: run the backward solve concurrently with the Gram / c-weighted Hessian sums (no gain measured on C3)
+#endif
+
 namespace rbo {
 
 #ifdef RBO_PHASE_TIMERS
@@ -64,6 +68,7 @@ struct K {
   double* cst;     // this CTA's coefficient tape in global memory: cst[k * NR + j] = cs[k][j] (rbs.jl:326)
   unsigned long long* mbar;
   unsigned qglob;  // running count of staged panel chunks (ring position and mbarrier parity)
+  int pipe_ncons;  // consumer warps the empty barriers currently expect (0 = not initialised)
   int *alist, *phase, *sstat, *siter, *stry, *sstart, *sevals, *sfr, *colidx, *items, *tbld;
 
   __device__ K(const DevProblem& P_, double* sm_) : P(P_), sm(sm_) {
@@ -72,7 +77,7 @@ struct K {
     nf = 0;
     CCOL = P.RP - 1; UCOL = P.RP - 2;
     V = sm + pl.V; Fp = sm + pl.Fp; G = sm + pl.G; u = sm + pl.u; Xs = sm + pl.Xs; stage = sm + pl.stage;
-    mbar = reinterpret_cast<unsigned long long*>(sm + pl.mbar); qglob = 0;
+    mbar = reinterpret_cast<unsigned long long*>(sm + pl.mbar); qglob = 0; pipe_ncons = 0;
     cst = P.cs_tape + (size_t)blockIdx.x * (P.h + 2) * P.NR;
     Xf = sm + pl.Xf; yf = sm + pl.yf; gyf = sm + pl.gyf; misc = sm + pl.misc; adj = sm + pl.adj; bestx = sm + pl.bestx;
     si = reinterpret_cast<int*>(sm + pl.ints);
@@ -123,7 +128,16 @@ struct K {
       double rho2 = 0.0;
       for (int p = 0; p < d; ++p) { double r = x[p] - xcoord(j, p); rho2 = fma(r, r, rho2); }
       double psi, a, b, gb;
-      kern_radial(P.kern, rho2, psi, a, b, gb);
+      if (P.kern.id == RBO_KERNEL_MATERN52) {
+        // closed forms without divisions: b = psi'/rho = -(c^2/3)(1+s)e^-s, a = (psi'' - b)/rho^2 = (c^4/3) e^-s; at rho = 0 they
+        // reduce to psi''(0) and a finite value that only ever multiplies r = 0 (rbf.jl:141-150)
+        const double cc = P.m52_c, c2 = cc * cc, s_ = cc * sqrt(rho2), e = exp(-s_);
+        psi = (1.0 + s_ * (1.0 + s_ * (1.0 / 3.0))) * e;
+        b = -(c2 * (1.0 / 3.0)) * (1.0 + s_) * e;
+        a = (c2 * c2 * (1.0 / 3.0)) * e;
+      } else {
+        kern_radial(P.kern, rho2, psi, a, b, gb);
+      }
       row[0] = psi;
       for (int p = 0; p < d; ++p) row[1 + p] = b * (x[p] - xcoord(j, p));
       row[d + 1] = a;
@@ -139,8 +153,8 @@ struct K {
   // A warp-task = (item, output block, row split); the RS partial sums are added in a fixed order by the consumer, so
   // results do not depend on scheduling.
   // ------------------------------------------------------------------------------------------------
-  __device__ int choose_rs(int nblocks) const {
-    int rs = RBO_NWARPS / (nblocks > 0 ? nblocks : 1);
+  __device__ int choose_rs(int nblocks, int nw = RBO_NWARPS) const {
+    int rs = nw / (nblocks > 0 ? nblocks : 1);
     return rs < 1 ? 1 : (rs > P.RSmax ? P.RSmax : rs);
   }
   __device__ __forceinline__ void set_item(int i, int colA, int na, int colB, int nb, int out) {
@@ -150,11 +164,12 @@ struct K {
   __device__ static __forceinline__ int nblk16(int n) { return (n + 15) >> 4; }
 
   // dst[rs * nout + item.out + p * nb + q]; nout = total number of outputs of this call (stride between row splits)
-  __device__ void colprod(int nitems, int nout, double* dst, int RS) {
+  __device__ void colprod(int nitems, int nout, double* dst, int RS, int wbase = 0, int nw = RBO_NWARPS) {
     const int RP = P.RP, nrows = P.N8 + nf, g = lane >> 2, tg = lane & 3;
     int ntask = 0;
     for (int i = 0; i < nitems; ++i) ntask += nblk16(items[5 * i + 1]) * nblk16(items[5 * i + 3]);
-    for (int task = warp; task < ntask * RS; task += RBO_NWARPS) {
+    if (warp < wbase || warp >= wbase + nw) return;
+    for (int task = warp - wbase; task < ntask * RS; task += nw) {
       int t = task / RS;
       const int rs = task - t * RS;
       int i = 0, nbA, nbB;
@@ -194,12 +209,13 @@ struct K {
   // Hk = a r r' + b I (rbf.jl:141-150): entries (p <= q) accumulate a r_p r_q, the b-weighted sums go to the extra entry T2.
   // phess[((rs * np + s) * 2 + which) * (T2 + 1) + e], which = 0 (c-weighted, rbs.jl:516-523) / 1 (w-weighted, rbs.jl:542-545).
   // Columns: (a, b) at cab(s) + d+1, d+2 ; w at cw(s) ; c in CCOL.
-  template <class PT, class CAB, class CW>
-  __device__ void hess_sums(int np, PT pt, CAB cab, CW cw, int RS) {
+  template <int MASK, class PT, class CAB, class CW>  // MASK bit 0: c-weighted sums (HC), bit 1: w-weighted sums (HW)
+  __device__ void hess_sums(int np, PT pt, CAB cab, CW cw, int RS, int wbase = 0, int nw = RBO_NWARPS) {
     const int d = P.d, RP = P.RP, T2 = d * (d + 1) / 2, nrows = P.N8 + nf, g = lane >> 2, tg = lane & 3;
     const int nbd = nblk16(d), nblk = nbd * (nbd + 1) / 2;  // upper-triangular 16 x 16 blocks
     double* out = sm + pl.phess;
-    for (int task = warp; task < np * nblk * RS; task += RBO_NWARPS) {
+    if (warp < wbase || warp >= wbase + nw) return;
+    for (int task = warp - wbase; task < np * nblk * RS; task += nw) {
       const int s = task / (nblk * RS), rem = task - s * nblk * RS, blk = rem / RS, rs = rem - blk * RS;
       int mb = 0, t = blk;
       while (t >= nbd - mb) { t -= nbd - mb; ++mb; }
@@ -217,18 +233,23 @@ struct K {
         const bool in = j < nrows;
         const int jj = in ? j : 0;
         const double* row = V + (size_t)jj * RP;
-        const double aj = in ? row[colab] : 0.0, bj = in ? row[colab + 1] : 0.0, wj = row[colw], cj = row[CCOL];
+        const double aj = in ? row[colab] : 0.0, bj = in ? row[colab + 1] : 0.0;
+        const double wj = (MASK & 2) ? row[colw] : 0.0, cj = (MASK & 1) ? row[CCOL] : 0.0;
         const double ca = cj * aj, wa = wj * aj;
         const double rp0 = xp0 - xcoord(jj, p0), rp1 = xp1 - xcoord(jj, p1), rq0 = xq0 - xcoord(jj, q0), rq1 = xq1 - xcoord(jj, q1_);
         if (g == 0) { bC = fma(cj, bj, bC); bW = fma(wj, bj, bW); }
-        dmma(cC[0][0], cC[0][1], ca * rp0, rq0);
-        dmma(cC[1][0], cC[1][1], ca * rp0, rq1);
-        dmma(cC[2][0], cC[2][1], ca * rp1, rq0);
-        dmma(cC[3][0], cC[3][1], ca * rp1, rq1);
-        dmma(cW[0][0], cW[0][1], wa * rp0, rq0);
-        dmma(cW[1][0], cW[1][1], wa * rp0, rq1);
-        dmma(cW[2][0], cW[2][1], wa * rp1, rq0);
-        dmma(cW[3][0], cW[3][1], wa * rp1, rq1);
+        if (MASK & 1) {
+          dmma(cC[0][0], cC[0][1], ca * rp0, rq0);
+          dmma(cC[1][0], cC[1][1], ca * rp0, rq1);
+          dmma(cC[2][0], cC[2][1], ca * rp1, rq0);
+          dmma(cC[3][0], cC[3][1], ca * rp1, rq1);
+        }
+        if (MASK & 2) {
+          dmma(cW[0][0], cW[0][1], wa * rp0, rq0);
+          dmma(cW[1][0], cW[1][1], wa * rp0, rq1);
+          dmma(cW[2][0], cW[2][1], wa * rp1, rq0);
+          dmma(cW[3][0], cW[3][1], wa * rp1, rq1);
+        }
       }
       bC += __shfl_xor_sync(FULL, bC, 1); bC += __shfl_xor_sync(FULL, bC, 2);
       bW += __shfl_xor_sync(FULL, bW, 1); bW += __shfl_xor_sync(FULL, bW, 2);
@@ -240,10 +261,14 @@ struct K {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int q = 16 * nk + 8 * (i & 1) + 2 * tg + e;
-          if (p <= q && q < d) { const int idx = tri_idx(p, q, d); oC[idx] = cC[i][e]; oW[idx] = cW[i][e]; }
+          if (p <= q && q < d) {
+            const int idx = tri_idx(p, q, d);
+            if (MASK & 1) oC[idx] = cC[i][e];
+            if (MASK & 2) oW[idx] = cW[i][e];
+          }
         }
       }
-      if (blk == 0 && lane == 0) { oC[T2] = bC; oW[T2] = bW; }
+      if (blk == 0 && lane == 0) { if (MASK & 1) oC[T2] = bC; if (MASK & 2) oW[T2] = bW; }
     }
   }
 
@@ -259,14 +284,24 @@ struct K {
   // ------------------------------------------------------------------------------------------------
   __device__ __forceinline__ unsigned smem_u32(const void* p) const { return (unsigned)__cvta_generic_to_shared(p); }
 
-  __device__ void mbar_init() {
+  // (Re)initialises the panel pipeline for `ncons` consumer warps. Must be called by all threads; no copy may be in flight.
+  __device__ void pipe_setup(int ncons) {
+    if (ncons == pipe_ncons) return;
+    __syncthreads();
     if (tid == 0) {
       for (int i = 0; i < RBO_NSTAGE; ++i) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[i])));                               // full: producer + tx bytes
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[RBO_NSTAGE + i])), "r"(RBO_NCONS));  // empty: one arrive per consumer warp
+        if (pipe_ncons != 0) {
+          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&mbar[i])));
+          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&mbar[RBO_NSTAGE + i])));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[i])));                           // full: producer + tx bytes
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[RBO_NSTAGE + i])), "r"(ncons));  // empty: one arrive per consumer warp
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pipe_ncons = ncons;
+    qglob = 0;
+    __syncthreads();
   }
   __device__ __forceinline__ void chunk_issue(unsigned q, const double* src, int ndoubles) {  // one thread
     const unsigned st = q % RBO_NSTAGE, mb = smem_u32(&mbar[st]), dst = smem_u32(stage + (size_t)st * RBO_CHUNK_K * RBO_LP);
@@ -364,6 +399,8 @@ struct K {
     const int ngroups = (ncols + 7) >> 3;
     const int nbatch = (ngroups + GPB - 1) / GPB;
     const unsigned chunks_per_pass = (unsigned)(nb * (nb + 1) / 2);
+    const int ncons = min(ngroups, GPB) * NRQ;  // consumer warps of this pass: warps 0 .. ncons-1
+    pipe_setup(ncons);
     if (warp == RBO_NCONS) {
       // ---------------- producer warp ----------------
       if (lane == 0) {
@@ -382,13 +419,14 @@ struct K {
       __syncwarp();
       return;
     }
+    if (warp >= ncons) return;  // not part of this pass: free for other work until the caller's next __syncthreads
     // ---------------- consumer warps ----------------
     const int g = lane >> 2, tg = lane & 3;
     const int gl = warp / NRQ, rq = warp - gl * NRQ;  // group slot within the batch, row quarter
     unsigned q = qglob;
     for (int bt = 0; bt < nbatch; ++bt) {
       const int group = bt * GPB + gl;
-      const bool wact = gl < GPB && group < ngroups;  // warp-uniform
+      const bool wact = group < ngroups;  // warp-uniform (false only in the last batch)
       // column offsets: cB for the B fragment (column g), c0/c1 for the C fragment (columns 2 tg, 2 tg + 1)
       const int i0 = 8 * group;
       const bool vB = wact && i0 + g < ncols, v0 = wact && i0 + 2 * tg < ncols, v1 = wact && i0 + 2 * tg + 1 < ncols;
@@ -434,7 +472,13 @@ struct K {
       for (int i = 0; i < nb; ++i) {
         const int ib = FWD ? i : nb - 1 - i, nc = FWD ? ib + 1 : nb - ib, rb = RBO_BR * ib;
         for (int cc = 0; cc < nc; ++cc, ++q) {
+#ifdef RBO_PHASE_TIMERS
+          long long tw0 = clock64();
+#endif
           full_wait(q);
+#ifdef RBO_PHASE_TIMERS
+          if (tid == 0) atomicAdd(&g_phase_cycles[FWD ? 12 : 13], (unsigned long long)(clock64() - tw0));
+#endif
           const double* buf = stage + (size_t)(q % RBO_NSTAGE) * RBO_CHUNK_K * RBO_LP + rofs;
           if (wact) {
             if (cc < nc - 1) {
@@ -506,21 +550,25 @@ struct K {
   // Writes sdmu, sdsig (grad sigma), sga (grad alpha), sHt (-(H alpha + mu-sigma cross term)), sHref (H alpha as the
   // reference computes it, Q1) and sgh = [alpha, g_mu, g_sig, g_muth, g_sigth, sigma, mu, finite].
   // ------------------------------------------------------------------------------------------------
-  __device__ void assemble_warp(int sl, int aidx, int np, int nout_pre, int nout_post, int post_off, int RSpre, int RSpost, int RShess, double fstar) {
+  // s2/tq come from `p1` (q1 outputs per point: |v0|^2, V_p.v0), the Gram V_p.V_q from `pg` (d x d per point).
+  __device__ void assemble_warp(int sl, int aidx, int np, int RSpre, const double* p1, int nout1, int RS1, const double* pg, int noutg, int goff, int gld,
+                                int RSg, int RShc, int RShw, double fstar) {
     const int d = P.d, dd = d * d, q1 = d + 1, T2 = d * (d + 1) / 2;
-    const double* ppre = sm + pl.ppre; const double* ppost = sm + pl.ppost; const double* phess = sm + pl.phess;
+    const double* ppre = sm + pl.ppre; const double* phess = sm + pl.phess;
+    const int nout_pre = np * q1;
     double* dmu = sm + pl.sdmu + sl * d; double* dsig = sm + pl.sdsig + sl * d; double* ga = sm + pl.sga + sl * d;
     double* Ht = sm + pl.sHt + sl * dd; double* Href = sm + pl.sHref + sl * dd; double* gh = sm + pl.sgh + sl * 8;
     auto pre = [&](int e) { double s = 0.0; for (int r = 0; r < RSpre; ++r) s += ppre[(size_t)r * nout_pre + aidx * q1 + e]; return s; };
-    auto post = [&](int p, int q) { double s = 0.0; for (int r = 0; r < RSpost; ++r) s += ppost[(size_t)r * nout_post + post_off + p * q1 + q]; return s; };
-    auto hes = [&](int which, int e) { double s = 0.0; for (int r = 0; r < RShess; ++r) s += phess[((size_t)(r * np + aidx) * 2 + which) * (T2 + 1) + e]; return s; };
+    auto one = [&](int e) { double s = 0.0; for (int r = 0; r < RS1; ++r) s += p1[(size_t)r * nout1 + e]; return s; };
+    auto gramf = [&](int p, int q) { double s = 0.0; for (int r = 0; r < RSg; ++r) s += pg[(size_t)r * noutg + goff + p * gld + q]; return s; };
+    auto hes = [&](int which, int e) { double s = 0.0; const int RS = which ? RShw : RShc; for (int r = 0; r < RS; ++r) s += phess[((size_t)(r * np + aidx) * 2 + which) * (T2 + 1) + e]; return s; };
     const double mu = pre(0);
-    const double var = P.k0 - post(0, 0);  // rbs.jl:528 (kx.w == |L^-1 kx|^2)
+    const double var = P.k0 - one(0);  // rbs.jl:528 (kx.w == |L^-1 kx|^2)
     const double sigma = sqrt(var), isg = 1.0 / sigma;
     const GPart g = rule_eval(P.rule_id, P.sigma_tol, mu, sigma, P.theta1, fstar);
     bool fin = isfinite(g.g);
     for (int p = lane; p < d; p += 32) {
-      double m = pre(1 + p), sg = -post(0, 1 + p) * isg;  // rbs.jl:514, 529
+      double m = pre(1 + p), sg = -one(1 + p) * isg;  // rbs.jl:514, 529
       double a = g.g_mu * m + g.g_sig * sg;            // rbs.jl:567
       dmu[p] = m; dsig[p] = sg; ga[p] = a;
       fin = fin && isfinite(a);
@@ -529,7 +577,7 @@ struct K {
     const double bC = hes(0, T2), bW = hes(1, T2);
     for (int e = lane; e < T2; e += 32) {
       const int pq = tbld[e], p = pq & 0xff, q = pq >> 8;
-      double gram = post(p + 1, q + 1), hc = hes(0, e), hw = hes(1, e);
+      double gram = gramf(p, q), hc = hes(0, e), hw = hes(1, e);
       if (p == q) { hc += bC; hw += bW; }
       double hs = (-dsig[p] * dsig[q] - gram - hw) * isg;                                                            // rbs.jl:541-546
       double href = g.g_mumu * dmu[p] * dmu[q] + g.g_mu * hc + g.g_sigsig * dsig[p] * dsig[q] + g.g_sig * hs;        // rbs.jl:568
@@ -723,11 +771,47 @@ struct K {
       __syncthreads();  // the solve below overwrites the raw columns in place
       PT_MARK(1);
       tri_solve<true>(nact * q1, nf);
+#if RBO_OVERLAP
+      for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS, 1, alist[s] * P.CS, q1, s * q1);  // |v0|^2, V_p.v0
+      __syncthreads();
+      PT_MARK(2);
+      const int RS1 = choose_rs(nact * nbq);
+      colprod(nact, nact * q1, sm + pl.ppost1, RS1);
+      __syncthreads();
+      for (int i = tid; i < nact; i += RBO_THREADS) colidx[i] = alist[i] * P.CS;
+      for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS + 1, d, alist[s] * P.CS + 1, d, s * d * d);  // V_p.V_q
+      __syncthreads();
+      PT_MARK(3);
+      // w = L^-T v0 (rbs.jl:525) on the few warps the backward pass can use; meanwhile the other consumer warps do the
+      // reductions that do not need w: the Gram matrix of V_g and the c-weighted Hessian sums
+      const int nbd = nblk16(d);
+      const int ngb = (nact + 7) >> 3, nwb = min((ngb * 4 <= RBO_NCONS) ? ngb * 4 : ((ngb * 2 <= RBO_NCONS) ? ngb * 2 : ngb), RBO_NCONS);
+      const int nwo = RBO_NCONS - nwb;
+      const bool overlap = RBO_OVERLAP && nwo >= 2 * nact;  // enough spare warps for the other reductions
+      const int RSg = overlap ? choose_rs(nact * nbd * nbd, nwo) : choose_rs(nact * nbd * nbd);
+      const int RShc = overlap ? choose_rs(nact * nbd * (nbd + 1) / 2, nwo) : choose_rs(nact * nbd * (nbd + 1) / 2);
+      tri_solve<false>(nact, nf);
+      if (overlap) {
+        colprod(nact, nact * d * d, sm + pl.ppost, RSg, nwb, nwo);
+        hess_sums<1>(nact, pt, cb, cb, RShc, nwb, nwo);
+      }
+      __syncthreads();
+      PT_MARK(4);
+      const int RShw = choose_rs(nact * nbd * (nbd + 1) / 2);
+      if (overlap) {
+        hess_sums<2>(nact, pt, cb, cb, RShw);
+      } else {
+        colprod(nact, nact * d * d, sm + pl.ppost, RSg);
+        hess_sums<3>(nact, pt, cb, cb, RShw);  // RShc == RShw here
+      }
+      __syncthreads();
+      PT_MARK(5);
+#else
       for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS, q1, alist[s] * P.CS, q1, s * q1 * q1);  // |v0|^2, V_p.v0, V_p.V_q
       __syncthreads();
       PT_MARK(2);
-      const int RSpost = choose_rs(nact * nbq * nbq);
-      colprod(nact, nact * q1 * q1, sm + pl.ppost, RSpost);
+      const int RS1 = choose_rs(nact * nbq * nbq), RSg = RS1;
+      colprod(nact, nact * q1 * q1, sm + pl.ppost, RS1);
       for (int i = tid; i < nact; i += RBO_THREADS) colidx[i] = alist[i] * P.CS;
       __syncthreads();
       PT_MARK(3);
@@ -735,14 +819,19 @@ struct K {
       __syncthreads();
       PT_MARK(4);
       const int nbd = nblk16(d);
-      const int RShess = choose_rs(nact * nbd * (nbd + 1) / 2);
-      hess_sums(nact, pt, cb, cb, RShess);
+      const int RShw = choose_rs(nact * nbd * (nbd + 1) / 2), RShc = RShw;
+      hess_sums<3>(nact, pt, cb, cb, RShw);
       __syncthreads();
       PT_MARK(5);
+#endif
       // per-start logic: one warp per active slot
       for (int s = warp; s < nact; s += RBO_NWARPS) {
         const int sl = alist[s];
-        assemble_warp(sl, s, nact, nact * q1, nact * q1 * q1, s * q1 * q1, RSpre, RSpost, RShess, misc[1]);
+#if RBO_OVERLAP
+        assemble_warp(sl, s, nact, RSpre, sm + pl.ppost1 + s * q1, nact * q1, RS1, sm + pl.ppost, nact * d * d, s * d * d, d, RSg, RShc, RShw, misc[1]);
+#else
+        assemble_warp(sl, s, nact, RSpre, sm + pl.ppost + s * q1 * q1, nact * q1 * q1, RS1, sm + pl.ppost, nact * q1 * q1, s * q1 * q1 + q1 + 1, q1, RSg, RShc, RShw, misc[1]);
+#endif
         slot_logic_warp(sl);
       }
       __syncthreads();
@@ -794,7 +883,6 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
   double* misc = k.misc;  // misc[0] best f, misc[1] fstar, misc[2..7] scalars, misc[8..] scratch
   int* si = k.si;
   k.build_tables();
-  k.mbar_init();
   for (int i = tid; i < NR * RP; i += RBO_THREADS) k.V[i] = 0.0;  // rows beyond the fantasy block are read (times exact zeros of L0's padding) but never written
   if (P.xsm) for (int i = tid; i < d * N8; i += RBO_THREADS) k.Xs[(i / N8) * P.XP + (i % N8)] = __ldg(P.Xb + i);
   __syncthreads();
@@ -1007,12 +1095,12 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
           k.tri_solve<false>(q1, k.nf);  // w = SOL[:,0], Dw = SOL[:,1..d] (rbs.jl:525-526)
           __syncthreads();
           const int RShess = k.choose_rs(nbd * (nbd + 1) / 2);
-          k.hess_sums(1, pt, cbr, cbs, RShess);
+          k.hess_sums<3>(1, pt, cbr, cbs, RShess);
           __syncthreads();
           if (k.warp == 0) {
             double fst = P.ymin_base;  // f* over the active slice y[1:N+i]
             for (int j = 0; j < i; ++j) fst = fmin(fst, k.yf[j]);
-            k.assemble_warp(0, 0, 1, q1, q1 * q1, 0, RSpre, RSpost, RShess, fst);
+            k.assemble_warp(0, 0, 1, RSpre, smem + k.pl.ppost, q1 * q1, RSpost, smem + k.pl.ppost, q1 * q1, q1 + 1, q1, RSpost, RShess, RShess, fst);
             if (tid == 0) {
               misc[2] = fst;
               // ---- solve_dual_x for j = i (rollout.jl:150-191) with the contributions of later solves already pushed ----

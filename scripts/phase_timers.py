@@ -1,13 +1,13 @@
 """Per-phase cycle breakdown of the rollout kernel (needs csrc/librbo_timers.so built with -DRBO_PHASE_TIMERS)."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["RBO_LIB_PATH"] = os.path.join(ROOT, "rollout-bayesian-optimization_b200", "csrc", "librbo_timers.so")
+os.environ["RBO_LIB_PATH"] = os.path.join(ROOT, "rollout-bayesian-optimization_b200", "csrc", os.environ.get("RBO_TIMERS_LIB", "librbo_timers.so"))
 sys.path.insert(0, ROOT)
 import numpy as np
 import __graft_entry__ as g
 
 NAMES = ["fill_columns", "reduce_pre", "fwd_solve", "reduce_post", "bwd_solve", "reduce_hess", "slot_logic", "bookkeeping",
-         "ts:sync", "round_gap", "draw+condition", "adjoint", "ts:issue", "ts:wait", "ts:compute(w0)", "rounds"]
+         "-", "round_gap", "draw+condition", "adjoint", "wait_full(fwd,w0)", "wait_full(bwd,w0)", "-", "rounds"]
 
 def main(name="C3", M=296):
     pkg = g.load_package()
