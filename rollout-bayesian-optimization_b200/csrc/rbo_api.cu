@@ -204,9 +204,9 @@ int rbo_set_surrogate(rbo_handle* h, int d, int N, const double* X, int ldX, con
     for (int k = 0; k < i; ++k) s -= Lij(i, k) * u0[k];
     u0[i] = s / Lij(i, i);
   }
-  // forward / backward 32-row panels with inverted diagonal blocks, k-major with pitch RBO_LP:
-  //   forward  panel ib: k = 0 .. 32 ib - 1 : L[32 ib + r][k]          ; then kk = 0..31 : Dinv_ib[r][kk]
-  //   backward panel ib: k' = 0 .. N32 - 32 (ib+1) - 1 : L[32 (ib+1) + k'][32 ib + r] ; then kk : Dinv_ib[kk][r]
+  // forward / backward 32-row panels, k-major with pitch RBO_LP (Dinv_ib = inverse of the 32x32 diagonal block):
+  //   forward  panel ib: k = 0 .. 32 ib - 1 : -(Dinv_ib L[32 ib .., k])[r]          ; then kk = 0..31 : Dinv_ib[r][kk]
+  //   backward panel ib: k' = 0 .. N32 - 32 (ib+1) - 1 : -(Dinv_ib' L[32 (ib+1) + k', 32 ib ..]')[r] ; then kk : Dinv_ib[kk][r]
   const int BR = RBO_BR, LP = RBO_LP, nb32 = (N + BR - 1) / BR, N32 = nb32 * BR;
   h->nb32 = nb32;
   const size_t nLf = (size_t)LP * BR * ((size_t)nb32 * (nb32 + 1) / 2), nLb = nLf;
@@ -220,16 +220,27 @@ int rbo_set_surrogate(rbo_handle* h, int d, int N, const double* X, int ldX, con
         for (int j = cc; j < rr; ++j) t -= Lij(r0 + rr, r0 + j) * Dinv[(size_t)j * BR + cc];
         Dinv[(size_t)rr * BR + cc] = (rr < cc) ? 0.0 : t / Lij(r0 + rr, r0 + rr);
       }
+    // The off-diagonal chunks are stored pre-multiplied by the inverted diagonal block and negated, so that a panel is one
+    // accumulation:  v_I = Dinv b_I - (Dinv L_{I,<I}) v_{<I}   (forward),   w_I = Dinv' b_I - (Dinv' L_{>I,I}') w_{>I}   (backward)
     double* pf = Lf.data() + (size_t)LP * BR * ((size_t)ib * (ib + 1) / 2);
     const int nk = BR * ib;
     for (int k = 0; k < nk; ++k)
-      for (int r = 0; r < BR; ++r) pf[(size_t)k * LP + r] = (r0 + r < N) ? Lij(r0 + r, k) : 0.0;
+      for (int r = 0; r < BR; ++r) {
+        double acc = 0.0;
+        for (int j = 0; j <= r; ++j) acc += Dinv[(size_t)r * BR + j] * ((r0 + j < N) ? Lij(r0 + j, k) : 0.0);
+        pf[(size_t)k * LP + r] = -acc;
+      }
     for (int kk = 0; kk < BR; ++kk)
       for (int r = 0; r < BR; ++r) pf[(size_t)(nk + kk) * LP + r] = Dinv[(size_t)r * BR + kk];
     double* pb = Lb.data() + (size_t)LP * BR * ((size_t)nb32 * ib - (size_t)ib * (ib - 1) / 2);
     const int k0 = BR * (ib + 1), nkb = N32 - k0;
     for (int kk = 0; kk < nkb; ++kk)
-      for (int r = 0; r < BR; ++r) pb[(size_t)kk * LP + r] = (k0 + kk < N && r0 + r < N) ? Lij(k0 + kk, r0 + r) : 0.0;
+      for (int r = 0; r < BR; ++r) {
+        double acc = 0.0;  // (Dinv' M)[r][kk] with M[j][kk] = L[k0 + kk][r0 + j], Dinv'[r][j] = Dinv[j][r] (j >= r)
+        if (k0 + kk < N)
+          for (int j = r; j < BR; ++j) acc += Dinv[(size_t)j * BR + r] * ((r0 + j < N) ? Lij(k0 + kk, r0 + j) : 0.0);
+        pb[(size_t)kk * LP + r] = -acc;
+      }
     for (int kk = 0; kk < BR; ++kk)
       for (int r = 0; r < BR; ++r) pb[(size_t)(nkb + kk) * LP + r] = Dinv[(size_t)kk * BR + r];
   }

@@ -485,19 +485,10 @@ struct K {
               const int krow0 = (FWD ? 0 : rb + RBO_BR) + cc * RBO_CHUNK_K;  // V row of the first k of this chunk
               mma_chunk<MTW>(buf, V + (size_t)krow0 * RP, cB, g, tg, c);
             } else {
-              // last chunk of the panel = inverted diagonal block: t = b - acc (in place), then rows <- Dinv t
-#pragma unroll
-              for (int mt = 0; mt < MTW; ++mt) {
-                const int row = rb + rofs + 8 * mt + g;
-                if (row < N8) {
-                  if (v0) V[(size_t)row * RP + c0] -= c[mt][0];
-                  if (v1) V[(size_t)row * RP + c1] -= c[mt][1];
-                }
-                c[mt][0] = 0.0; c[mt][1] = 0.0;
-              }
-              group_sync(NRQ, gl);  // every t row of the panel is in place
+              // last chunk of the panel = inverted diagonal block applied to the panel's own right-hand-side rows; the
+              // off-diagonal chunks were pre-multiplied by it and negated on the host, so c now holds the solved rows
               mma_chunk<MTW>(buf, V + (size_t)rb * RP, cB, g, tg, c);
-              group_sync(NRQ, gl);  // every warp of the group has read t
+              group_sync(NRQ, gl);  // every warp of the group has read the right-hand-side rows
 #pragma unroll
               for (int mt = 0; mt < MTW; ++mt) {
                 const int row = rb + rofs + 8 * mt + g;
