@@ -182,3 +182,91 @@ def test_api_errors_are_loud(pkg):
             eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, 9, 0.0, np.zeros(8))
     finally:
         eng.close()
+
+
+ORC_KERNEL = {"Matern52": "matern52", "Matern32": "matern32", "Matern12": "matern12", "SquaredExponential": "se", "Periodic": "periodic"}
+
+
+def custom_case(pkg, orc, d, N, h, M, S, kernel, ktheta, rule, theta, seed=5):
+    """A GP-prior workload with an arbitrary kernel / decision rule (the BASELINE configs all use Matern-5/2 + EI)."""
+    rng = np.random.default_rng(seed)
+    X = np.asfortranarray(rng.random((d, N)))
+    psi = getattr(pkg, kernel)(list(ktheta))
+    K = pkg.eval_KXX(psi, X, 1e-6)
+    y = np.linalg.cholesky(K) @ rng.standard_normal(N)
+    g = {"EI": pkg.EI(), "POI": pkg.POI(), "LCB": pkg.LCB()}[rule]
+    sur = pkg.Surrogate(psi, X, y, capacity=N + 3, decision_rule=g, σn2=1e-6)
+    lbs, ubs, x0 = np.zeros(d), np.ones(d), np.full(d, 0.5)
+    rn = orc.gen_low_discrepancy_sequence(M, d, h + 1)
+    starts = orc.generate_initial_guesses(S, lbs, ubs)
+    dd = np.asfortranarray(rng.random((d, max(h, 1), M)))
+    N_ = sur.observed
+    P = orc.OracleProblem(sur.X[:, :N_], sur.L[:N_, :N_], sur.y[:N_], sur.c[:N_], x0, lbs, ubs, rn, starts, h=h,
+                          kernel=ORC_KERNEL[kernel], ktheta=tuple(ktheta), rule=rule, theta=theta, sigma_n2=1e-6,
+                          sigma_tol=g.σtol, fmini=float(np.min(sur.y)), mode=1, dual_dirs=dd)
+    return sur, P, rn, starts, dd, lbs, ubs, x0
+
+
+def run_custom(pkg, sur, rn, starts, dd, lbs, ubs, x0, theta, h, x_forced=None, htol=None):
+    eng = pkg.RolloutEngine(0)
+    try:
+        if htol is not None:
+            eng.set_htol(htol)
+        eng.set_surrogate(pkg.FantasySurrogate(sur, h))
+        eng.set_normals(rn)
+        eng.set_starts(starts)
+        M, d = rn.shape[0], len(x0)
+        out = dict(values=np.zeros(M), grad_x=np.zeros((d, M), order="F"), grad_theta=np.zeros((len(theta), M), order="F"),
+                   best_index=np.zeros(M, np.int32), grad_case=np.zeros(M, np.int32), status=np.zeros(M, np.int32))
+        eng.rollout(x0, theta, lbs, ubs, h, float(np.min(sur.y)), out["values"], out["grad_x"], out["grad_theta"], dual_dirs=dd,
+                    x_forced=x_forced, best_index=out["best_index"], grad_case=out["grad_case"], status=out["status"])
+        out.update(eng.tape(h))
+        return out
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("kernel,ktheta,rule,theta", [
+    ("Matern32", (0.45,), "EI", (0.0,)), ("Matern12", (0.6,), "EI", (0.01,)), ("SquaredExponential", (0.35,), "EI", (0.0,)),
+    ("Periodic", (0.9, 1.7), "EI", (0.0,)), ("Matern52", (0.4,), "POI", (0.0,)), ("Matern52", (0.4,), "LCB", (2.0,)),
+    ("SquaredExponential", (0.35,), "POI", (0.05,))])
+def test_other_kernels_and_rules(pkg, orc, kernel, ktheta, rule, theta):
+    """rbf.jl:60-103 kernels and decision_rules.jl:84-127 rules: step-level (teacher-forced) parity incl. the adjoint, and
+    free-running values."""
+    d, N, h, M, S = 3, 18, 3, 48, 4
+    sur, P, rn, starts, dd, lbs, ubs, x0 = custom_case(pkg, orc, d, N, h, M, S, kernel, ktheta, rule, theta)
+    P.p.htol = -np.inf
+    ref = P.rollout()
+    got = run_custom(pkg, sur, rn, starts, dd, lbs, ubs, x0, np.array(theta), h, x_forced=np.asfortranarray(ref["xs"][:, 1:, :]), htol=-np.inf)
+    assert np.array_equal(got["status"], ref["status"])
+    ok = ref["status"] == 0
+    if kernel == "Matern12":
+        # psi''(0) = 1/l^2 > 0 makes the gradient block of Dk(0) negative (rbf.jl:152-159): the joint value/gradient covariance is
+        # not positive definite and the reference throws PosDefException (rbs.jl:537) on every sample; both sides must say so
+        assert np.all(ref["status"] == 3) and np.all(got["status"] == 3)
+        return
+    assert ok.sum() >= M // 2
+    assert relerr(got["ys"][:, ok], ref["ys"][:, ok]) < 1e-8 and relerr(got["values"][ok], ref["values"][ok]) < 1e-8
+    assert np.array_equal(got["grad_case"][ok], ref["grad_case"][ok])
+    gscale = np.maximum(np.abs(ref["grad_x"]).max(axis=0, keepdims=True), 1e-6)
+    gerr = np.max(np.abs(got["grad_x"] - ref["grad_x"]) / gscale, axis=0)[ok]
+    assert np.mean(gerr < 1e-5) >= 0.97, np.sort(gerr)[-5:]
+    free = run_custom(pkg, sur, rn, starts, dd, lbs, ubs, x0, np.array(theta), h, htol=-np.inf)
+    fv, ev = frac_within(free["values"][ok], ref["values"][ok], 1e-7, 1.0)
+    assert fv >= 0.95, ev
+
+
+@pytest.mark.parametrize("d,N,h,S", [(1, 9, 2, 3), (20, 40, 1, 3), (31, 33, 1, 2), (4, 97, 7, 3)])
+def test_dimension_extremes(pkg, orc, d, N, h, S):
+    """d = 1, d > 16 (more than one 16 x 16 output block), d = 31, the longest supported horizon and a ragged last panel."""
+    M = 24
+    sur, P, rn, starts, dd, lbs, ubs, x0 = custom_case(pkg, orc, d, N, h, M, S, "Matern52", (0.6 * np.sqrt(d),), "EI", (0.0,))
+    ref = P.rollout()
+    got = run_custom(pkg, sur, rn, starts, dd, lbs, ubs, x0, np.zeros(1), h, x_forced=np.asfortranarray(ref["xs"][:, 1:, :]))
+    assert np.array_equal(got["status"], ref["status"])
+    assert relerr(got["ys"], ref["ys"]) < 1e-8 and relerr(got["values"], ref["values"]) < 1e-8
+    gscale = np.maximum(np.abs(ref["grad_x"]).max(axis=0, keepdims=True), 1e-6)
+    assert np.max(np.abs(got["grad_x"] - ref["grad_x"]) / gscale) < 1e-5
+    free = run_custom(pkg, sur, rn, starts, dd, lbs, ubs, x0, np.zeros(1), h)
+    fv, ev = frac_within(free["values"], ref["values"], 1e-7, 1.0)
+    assert fv >= 0.95, ev
