@@ -56,6 +56,7 @@ struct rbo_handle {
   int sums_len = 0;
   double *dual_dirs = nullptr, *x_forced = nullptr, *cs_tape = nullptr;
   size_t dual_cap = 0, forced_cap = 0, tape_cap = 0;
+  size_t cap_Xb = 0, cap_yb = 0, cap_c0 = 0, cap_u0 = 0, cap_Lf = 0, cap_Lb = 0, cap_rn = 0, cap_starts = 0;
   // last call
   int last_h = 0, last_mode = 0, last_nth = 1;
   bool tape_enabled = true;
@@ -83,6 +84,14 @@ static cudaError_t dev_realloc(T** p, size_t n) {
   if (*p) { cudaFree(*p); *p = nullptr; }
   if (n == 0) return cudaSuccess;
   return cudaMalloc((void**)p, n * sizeof(T));
+}
+// grows only: cudaFree / cudaMalloc synchronise the device and cost ~0.1 s on a busy context
+template <class T>
+static cudaError_t dev_reserve(T** p, size_t* cap, size_t n) {
+  if (*p && *cap >= n) return cudaSuccess;
+  cudaError_t e = dev_realloc(p, n);
+  *cap = (e == cudaSuccess) ? n : 0;
+  return e;
 }
 
 extern "C" {
@@ -244,12 +253,12 @@ int rbo_set_surrogate(rbo_handle* h, int d, int N, const double* X, int ldX, con
     for (int kk = 0; kk < BR; ++kk)
       for (int r = 0; r < BR; ++r) pb[(size_t)(nkb + kk) * LP + r] = Dinv[(size_t)kk * BR + r];
   }
-  CK(h, dev_realloc(&h->Xb, Xb.size()));
-  CK(h, dev_realloc(&h->yb, (size_t)N));
-  CK(h, dev_realloc(&h->c0, (size_t)N8));
-  CK(h, dev_realloc(&h->u0, (size_t)N8));
-  CK(h, dev_realloc(&h->Lf, nLf));
-  CK(h, dev_realloc(&h->Lb, nLb));
+  CK(h, dev_reserve(&h->Xb, &h->cap_Xb, Xb.size()));
+  CK(h, dev_reserve(&h->yb, &h->cap_yb, (size_t)N));
+  CK(h, dev_reserve(&h->c0, &h->cap_c0, (size_t)N8));
+  CK(h, dev_reserve(&h->u0, &h->cap_u0, (size_t)N8));
+  CK(h, dev_reserve(&h->Lf, &h->cap_Lf, nLf));
+  CK(h, dev_reserve(&h->Lb, &h->cap_Lb, nLb));
   CK(h, cudaMemcpyAsync(h->Xb, Xb.data(), Xb.size() * 8, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->yb, y, (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->c0, c0.data(), (size_t)N8 * 8, cudaMemcpyHostToDevice, h->stream));
@@ -267,7 +276,7 @@ int rbo_set_normals(rbo_handle* h, const double* rn, int M_total, int hp1, int m
   if (!rn || M_total < 1 || hp1 < 1 || m_begin < 0 || m_count < 1 || m_begin + m_count > M_total) return fail(h, RBO_ERR_ARG, "rbo_set_normals: bad arguments");
   CK(h, cudaSetDevice(h->device));
   const int q1 = h->d + 1;
-  CK(h, dev_realloc(&h->rn, (size_t)m_count * q1 * hp1));
+  CK(h, dev_reserve(&h->rn, &h->cap_rn, (size_t)m_count * q1 * hp1));
   // strided slice [m_begin, m_begin+m_count) of the sample-fastest tensor
   CK(h, cudaMemcpy2DAsync(h->rn, (size_t)m_count * 8, rn + m_begin, (size_t)M_total * 8, (size_t)m_count * 8, (size_t)q1 * hp1, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
@@ -283,7 +292,7 @@ int rbo_generate_normals(rbo_handle* h, int M_total, int hp1, int m_begin, int m
   if (D > RBO_SOBOL_MAXDIM) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_generate_normals: %d Sobol dimensions > %d", D, RBO_SOBOL_MAXDIM);
   if ((double)M_total * hp1 >= 4294967295.0) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_generate_normals: more than 2^32 Sobol points");
   CK(h, cudaSetDevice(h->device));
-  CK(h, dev_realloc(&h->rn, (size_t)m_count * q1 * hp1));
+  CK(h, dev_reserve(&h->rn, &h->cap_rn, (size_t)m_count * q1 * hp1));
   size_t total = (size_t)m_count * q1 * hp1;
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
   rbo_normals_kernel<<<blocks, 256, 0, h->stream>>>(h->sobol_dirs, h->rn, M_total, h->d, hp1, m_begin, m_count);
@@ -306,7 +315,7 @@ int rbo_set_starts(rbo_handle* h, const double* starts, int S) {
   if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_set_starts: call rbo_set_surrogate first");
   if (!starts || S < 1) return fail(h, RBO_ERR_ARG, "rbo_set_starts: bad arguments");
   CK(h, cudaSetDevice(h->device));
-  CK(h, dev_realloc(&h->starts, (size_t)S * h->d));
+  CK(h, dev_reserve(&h->starts, &h->cap_starts, (size_t)S * h->d));
   CK(h, cudaMemcpyAsync(h->starts, starts, (size_t)S * h->d * 8, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   h->S = S;
