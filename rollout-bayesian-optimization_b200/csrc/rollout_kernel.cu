@@ -823,7 +823,14 @@ struct K {
 #else
         assemble_warp(sl, s, nact, RSpre, sm + pl.ppost + s * q1 * q1, nact * q1 * q1, RS1, sm + pl.ppost, nact * q1 * q1, s * q1 * q1 + q1 + 1, q1, RSg, RShc, RShw, misc[1]);
 #endif
+#ifdef RBO_PHASE_TIMERS
+        long long ta_ = clock64();
+        if (tid == 0) atomicAdd(&g_phase_cycles[8], (unsigned long long)(ta_ - pt_t0));
+#endif
         slot_logic_warp(sl);
+#ifdef RBO_PHASE_TIMERS
+        if (tid == 0) atomicAdd(&g_phase_cycles[14], (unsigned long long)(clock64() - ta_));
+#endif
       }
       __syncthreads();
       PT_MARK(6);

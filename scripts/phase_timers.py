@@ -7,7 +7,7 @@ import numpy as np
 import __graft_entry__ as g
 
 NAMES = ["fill_columns", "reduce_pre", "fwd_solve", "reduce_post", "bwd_solve", "reduce_hess", "slot_logic", "bookkeeping",
-         "-", "round_gap", "draw+condition", "adjoint", "wait_full(fwd,w0)", "wait_full(bwd,w0)", "-", "rounds"]
+         "  logic:assemble(w0)", "round_gap", "draw+condition", "adjoint", "wait_full(fwd,w0)", "wait_full(bwd,w0)", "  logic:solver(w0)", "rounds"]
 
 def main(name="C3", M=296):
     pkg = g.load_package()
