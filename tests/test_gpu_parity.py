@@ -270,3 +270,51 @@ def test_dimension_extremes(pkg, orc, d, N, h, S):
     free = run_custom(pkg, sur, rn, starts, dd, lbs, ubs, x0, np.zeros(1), h)
     fv, ev = frac_within(free["values"], ref["values"], 1e-7, 1.0)
     assert fv >= 0.95, ev
+
+
+@pytest.mark.parametrize("h,M,S", [(0, 17, 3), (1, 1, 1), (2, 149, 2)])
+def test_edge_shapes(pkg, orc, h, M, S):
+    """horizon 0 (no inner solve: cases 1/2 only), a single trajectory with a single start, M not a multiple of the grid."""
+    d, N = 3, 14
+    sur, P, rn, starts, dd, lbs, ubs, x0 = custom_case(pkg, orc, d, N, h, M, S, "Matern52", (0.5,), "EI", (0.0,), seed=9)
+    starts = np.asfortranarray(starts[:, :S])  # drop the two corner starts: exactly S columns
+    P = orc.OracleProblem(sur.X[:, :N], sur.L[:N, :N], sur.y[:N], sur.c[:N], x0, lbs, ubs, rn, starts, h=h, kernel="matern52",
+                          ktheta=(0.5,), rule="EI", theta=(0.0,), sigma_n2=1e-6, fmini=float(np.min(sur.y)), mode=1, dual_dirs=dd)
+    ref = P.rollout()
+    got = run_custom(pkg, sur, rn, starts, dd, lbs, ubs, x0, np.zeros(1), h)
+    assert np.array_equal(got["status"], ref["status"]) and np.array_equal(got["grad_case"], ref["grad_case"])
+    fv, ev = frac_within(got["values"], ref["values"], 1e-8, 1.0)
+    assert fv == 1.0, ev
+    gscale = np.maximum(np.abs(ref["grad_x"]).max(axis=0, keepdims=True), 1e-6)
+    assert np.max(np.abs(got["grad_x"] - ref["grad_x"]) / gscale) < 1e-5
+    if h == 0:
+        assert set(np.unique(ref["grad_case"])) <= {1, 2}
+
+
+def test_sga_loop_matches_oracle_driven_loop(pkg, orc):
+    """stochastic_solve (utils.jl:235-265 with Adam, optimizers.jl:48-75): the device keeps surrogate/normals/starts resident
+    and only x0 changes; the same loop driven by the oracle must produce the same iterates."""
+    wl = pkg.problems.make_workload("GP:2:0.25", M=64, N=12, h=2, S=3)
+    sur = wl.surrogate()
+    fs = pkg.FantasySurrogate(sur, wl.h)
+    T = pkg.Trajectory(sur, fs, start=wl.x0, hypers=wl.theta, horizon=wl.h)
+    rn = orc.gen_low_discrepancy_sequence(wl.M, wl.d, wl.h + 1)
+    tp = pkg.TrajectoryParameters(wl.x0, wl.theta, wl.h, wl.M, False, wl.lbs, wl.ubs, rnstream_sequence=rn)
+    es = pkg.ExperimentSetup(tp, wl.S)
+    dd = np.asfortranarray(np.random.default_rng(3).random((wl.d, wl.h, wl.M)))
+    iters = 6
+    xg, hist = pkg.stochastic_solve(pkg.Adam(η=0.02), T, tp, es, wl.x0, max_iterations=iters, use_eswavs=False, dual_directions=dd)
+    # oracle-driven loop
+    x = wl.x0.copy()
+    opt = pkg.Adam(η=0.02)
+    for it in range(iters):
+        wl_it = wl
+        P = orc.OracleProblem(sur.X[:, :wl.N], sur.L[:wl.N, :wl.N], sur.y[:wl.N], sur.c[:wl.N], x, wl.lbs, wl.ubs, rn, es.inner_solve_xstarts,
+                              h=wl.h, kernel="matern52", ktheta=(wl.ell,), rule="EI", theta=wl.theta, sigma_n2=wl.sigma_n2,
+                              fmini=float(np.min(sur.y)), mode=1, dual_dirs=dd)
+        r = P.rollout(tape=False)
+        g = r["grad_x"].mean(axis=1)
+        assert relerr(hist[it][0], x) < 1e-7 and abs(hist[it][1] - r["values"].mean()) < 1e-8
+        assert np.max(np.abs(hist[it][2] - g)) <= 1e-5 * max(1.0, np.abs(g).max())
+        pkg.update_optimizer(opt, x, g)
+    assert relerr(xg, x) < 1e-6
