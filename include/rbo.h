@@ -39,7 +39,11 @@ enum { RBO_RULE_EI = 0, RBO_RULE_POI = 1, RBO_RULE_LCB = 2 };
 /* which outputs rbo_rollout computes: resolutions only, or resolutions + gradient(T) (rollout.jl:318-323) */
 enum { RBO_MODE_VALUE = 0, RBO_MODE_VALUE_GRAD = 1 };
 /* flags */
-enum { RBO_FLAG_TEACHER_FORCED = 1 /* x_1..x_h supplied by the caller (step-level parity tests) */ };
+enum {
+  RBO_FLAG_TEACHER_FORCED = 1, /* x_1..x_h supplied by the caller (step-level parity tests) */
+  RBO_FLAG_GAUSS_HERMITE = 2   /* simulate_trajectory_ghq (rollout.jl:409-467): GaussHermiteObservable draws (observables.jl:32-81,157)
+                                  from the nodes / weights of rbo_set_quadrature instead of the normals */
+};
 
 /* per-trajectory status: what the reference would have thrown for that sample */
 enum {
@@ -110,6 +114,10 @@ int rbo_set_normals(rbo_handle* h, const double* rn, int M_total, int hp1, int m
 int rbo_generate_normals(rbo_handle* h, int M_total, int hp1, int m_begin, int m_count);
 /* Copies the handle's normals back: out is m_count x (d+1) x hp1 column-major. */
 int rbo_get_normals(rbo_handle* h, double* out);
+/* Quadrature data of simulate_trajectory_ghq (rollout.jl:409-467): for sample i the reference sets the observable's
+ * nodes / weights to nodes[indices[i]], weights[indices[i]] (rollout.jl:431-432). nodes, weights: depth x m_count,
+ * column-major (step fastest), depth >= horizon + 1. Used by rbo_rollout with RBO_FLAG_GAUSS_HERMITE. */
+int rbo_set_quadrature(rbo_handle* h, const double* nodes, const double* weights, int depth, int m_count);
 /* inner_solve_xstarts (rollout.jl:282): d x S, S = number of columns (the reference passes S+2). */
 int rbo_set_starts(rbo_handle* h, const double* starts, int S);
 

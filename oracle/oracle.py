@@ -15,7 +15,7 @@ _LIB = None
 
 KERNEL_IDS = {"matern12": 0, "matern32": 1, "matern52": 2, "se": 3, "periodic": 4}
 RULE_IDS = {"EI": 0, "POI": 1, "LCB": 2}
-FLAG_TEACHER_FORCED, FLAG_FAST_PERTURB, FLAG_FACTORED = 1, 2, 4
+FLAG_TEACHER_FORCED, FLAG_FAST_PERTURB, FLAG_FACTORED, FLAG_GAUSS_HERMITE = 1, 2, 4, 8
 
 
 class SolverOpts(C.Structure):
@@ -36,7 +36,7 @@ class Problem(C.Structure):
                 ("x0", _dp), ("theta", _dp), ("ntheta", C.c_int), ("lbs", _dp), ("ubs", _dp),
                 ("fmini", C.c_double), ("rn", _dp), ("rn_hp1", C.c_int), ("starts", _dp),
                 ("dual_dirs", _dp), ("x_forced", _dp), ("mode", C.c_int), ("flags", C.c_int),
-                ("htol", C.c_double), ("solver", SolverOpts), ("nthreads", C.c_int)]
+                ("htol", C.c_double), ("solver", SolverOpts), ("nthreads", C.c_int), ("gh_nodes", _dp), ("gh_weights", _dp)]
 
 
 class Outputs(C.Structure):
@@ -106,7 +106,7 @@ class OracleProblem:
 
     def __init__(self, X, L, y, c, x0, lbs, ubs, rn, starts, *, h, kernel="matern52", ktheta=(1.0,), rule="EI",
                  theta=(0.0,), sigma_n2=1e-6, sigma_tol=1e-8, fmini=None, mode=1, flags=0, dual_dirs=None,
-                 x_forced=None, htol=1e-4, nthreads=0, solver=None):
+                 x_forced=None, htol=1e-4, nthreads=0, solver=None, gh_nodes=None, gh_weights=None):
         self.X = np.asfortranarray(X, dtype=np.float64)
         self.d, self.N = self.X.shape
         self.L = np.asfortranarray(L, dtype=np.float64)
@@ -135,6 +135,12 @@ class OracleProblem:
         p.rn, p.rn_hp1, p.starts = _ptr(self.rn), self.rn.shape[2], _ptr(self.starts)
         p.dual_dirs, p.x_forced = _ptr(self.dual_dirs), _ptr(self.x_forced)
         p.mode, p.flags, p.htol, p.nthreads = mode, flags, htol, nthreads
+        self.gh_nodes = None if gh_nodes is None else np.asfortranarray(gh_nodes, dtype=np.float64)      # (h+1) x M
+        self.gh_weights = None if gh_weights is None else np.asfortranarray(gh_weights, dtype=np.float64)
+        p.gh_nodes, p.gh_weights = _ptr(self.gh_nodes), _ptr(self.gh_weights)
+        if self.gh_nodes is not None:
+            p.flags |= FLAG_GAUSS_HERMITE
+            assert self.gh_nodes.shape == (h + 1, self.M)
         p.solver = solver if solver is not None else default_solver_opts()
         self.p = p
 

@@ -382,6 +382,16 @@ void reset_fs(FS& fs) {  // rbs.jl:476-480
   fs.cs.resize(1);
 }
 
+// GaussHermiteObservable functor (observables.jl:54-64): y = mu + sqrt(2) sigma node, grad y = grad mu + sqrt(2) grad sigma node
+int gh_draw(const Ctx& cx, const FS& fs, const double* x, const double* theta, int fantasy_index, double node, double* out) {
+  SX s;
+  eval_fs(cx, fs, x, theta, fantasy_index, 1, s);
+  const double sqrt2 = 1.4142135623730951;
+  out[0] = s.mu + sqrt2 * s.sigma * node;
+  for (int a = 0; a < fs.d; ++a) out[1 + a] = s.dmu[a] + sqrt2 * s.dsig[a] * node;
+  return s.neg_var ? ORC_NEG_VARIANCE : ORC_OK;
+}
+
 // gp_draw with gradient: rbs.jl:588-611 using sx.dmu (rbs.jl:515) and sx.dsigma (rbs.jl:530-539).
 // out[0] = y, out[1..d] = grad y.
 int gp_draw(const Ctx& cx, const FS& fs, const double* x, const double* theta, int fantasy_index, const double* z, double* out) {
@@ -876,8 +886,13 @@ int orc_rollout(const orc_problem* p, orc_outputs* out) {
           xloc = xnext.data();
         }
         // StochasticObservable functor (observables.jl:106-121): z = stdnormal[:, step+1], fantasy_index = step-1
-        for (int k = 0; k < q; ++k) z[k] = p->rn[(size_t)m + (size_t)M * k + (size_t)M * q * step];
-        int ds = gp_draw(cx, fs, xloc, p->theta, step - 1, z.data(), draw.data());
+        int ds;
+        if (p->flags & ORC_FLAG_GAUSS_HERMITE) {
+          ds = gh_draw(cx, fs, xloc, p->theta, step - 1, p->gh_nodes[(size_t)m * (h + 1) + step], draw.data());
+        } else {
+          for (int k = 0; k < q; ++k) z[k] = p->rn[(size_t)m + (size_t)M * k + (size_t)M * q * step];
+          ds = gp_draw(cx, fs, xloc, p->theta, step - 1, z.data(), draw.data());
+        }
         if (ds != ORC_OK && status == ORC_OK) status = ds;
         tj.obs[step] = draw[0];
         for (int a = 0; a < d; ++a) tj.grads[(size_t)step * d + a] = draw[1 + a];
@@ -886,8 +901,16 @@ int orc_rollout(const orc_problem* p, orc_outputs* out) {
       }
       // resolve (rollout.jl:108-111; observables.jl:12-14)
       double best = tj.obs[0];
-      for (int k = 1; k <= h; ++k) best = std::min(best, tj.obs[k]);
+      int kbest = 0;
+      for (int k = 1; k <= h; ++k) if (tj.obs[k] < best) { best = tj.obs[k]; kbest = k; }
       out->values[m] = std::max(p->fmini - best, 0.0);
+      if (p->flags & ORC_FLAG_GAUSS_HERMITE) {
+        // resolve(gho; fmini) (observables.jl:66-72): weight of the best step, 1/sqrt(pi); get_gradient (observables.jl:157,
+        // the later definition wins): weights[at] * gradients[:, at]
+        out->values[m] = p->gh_weights[(size_t)m * (h + 1) + kbest] * std::max(p->fmini - best, 0.0) / 1.7724538509055159;
+        for (int k = 0; k <= h; ++k)
+          for (int a = 0; a < d; ++a) tj.grads[(size_t)k * d + a] *= p->gh_weights[(size_t)m * (h + 1) + k];
+      }
       int tcase = 0, tbest = 0;
       {
         double fb = tj.obs[0];

@@ -22,7 +22,8 @@ enum { ORC_MODE_VALUE = 0, ORC_MODE_VALUE_GRAD = 1 };
 enum {
   ORC_FLAG_TEACHER_FORCED = 1,  /* x_1..x_h taken from x_forced instead of the inner solve */
   ORC_FLAG_FAST_PERTURB = 2,    /* rank-2 shortcut for dK*v instead of the reference's dense build */
-  ORC_FLAG_FACTORED = 4         /* sigma^2 = k0 - |L^-1 kx|^2 etc. (forward-solve formulation) */
+  ORC_FLAG_FACTORED = 4,        /* sigma^2 = k0 - |L^-1 kx|^2 etc. (forward-solve formulation) */
+  ORC_FLAG_GAUSS_HERMITE = 8    /* GaussHermiteObservable (observables.jl:32-81,157) instead of StochasticObservable */
 };
 /* per-trajectory status */
 enum {
@@ -70,6 +71,8 @@ typedef struct {
   double htol;                /* rollout.jl:156 */
   orc_solver_opts solver;
   int nthreads;               /* <=0: all */
+  const double* gh_nodes;     /* (h+1) x M: nodes[indices[m]] of simulate_trajectory_ghq (rollout.jl:431-432), step fastest */
+  const double* gh_weights;   /* (h+1) x M */
 } orc_problem;
 
 typedef struct {

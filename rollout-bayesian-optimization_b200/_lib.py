@@ -39,6 +39,7 @@ SYMBOLS = {
     "rbo_set_normals": (C.c_int, [C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "rbo_generate_normals": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "rbo_get_normals": (C.c_int, [C.c_void_p, _dp]),
+    "rbo_set_quadrature": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int, C.c_int]),
     "rbo_set_starts": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "rbo_rollout": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_int, _dp, _dp,
                               _dp, _dp, _dp, _ip, _ip, _ip, C.POINTER(Summary)]),

@@ -444,17 +444,25 @@ class RolloutEngine:
         self.handle.check(self.lib.rbo_get_normals(self.handle.h, dptr(out)))
         return out
 
+    def set_quadrature(self, nodes, weights):
+        """nodes, weights: depth x M (column m = nodes[indices[m]] of rollout.jl:431-432)."""
+        nodes = np.asfortranarray(nodes, dtype=np.float64); weights = np.asfortranarray(weights, dtype=np.float64)
+        if nodes.shape != weights.shape or nodes.ndim != 2:
+            raise ValueError("nodes and weights must both be depth x M")
+        self.handle.check(self.lib.rbo_set_quadrature(self.handle.h, dptr(nodes), dptr(weights), nodes.shape[0], nodes.shape[1]))
+        self.m_count = nodes.shape[1]
+
     def set_starts(self, starts):
         starts = np.asfortranarray(starts, dtype=np.float64)
         self.handle.check(self.lib.rbo_set_starts(self.handle.h, dptr(starts), starts.shape[1]))
         self.S = starts.shape[1]
 
     def rollout(self, x0, theta, lbs, ubs, horizon, fmini, values, grad_x=None, grad_theta=None, dual_dirs=None,
-                x_forced=None, best_index=None, grad_case=None, status=None):
+                x_forced=None, best_index=None, grad_case=None, status=None, gauss_hermite=False):
         x0 = np.ascontiguousarray(x0, dtype=np.float64); theta = np.ascontiguousarray(theta, dtype=np.float64)
         lbs = np.ascontiguousarray(lbs, dtype=np.float64); ubs = np.ascontiguousarray(ubs, dtype=np.float64)
         mode = 1 if (grad_x is not None and grad_theta is not None) else 0  # rollout.jl:319
-        flags = 1 if x_forced is not None else 0
+        flags = (1 if x_forced is not None else 0) | (2 if gauss_hermite else 0)
         if dual_dirs is not None:
             dual_dirs = np.asfortranarray(dual_dirs, dtype=np.float64)
         if x_forced is not None:
@@ -552,6 +560,66 @@ def simulate_trajectory_mc(T, tp, *, inner_solve_xstarts, resolutions, spatial_g
     gx, sgx = _mean_std_rows(spatial_gradients_container)
     gt, sgt = _mean_std_rows(hyperparameter_gradients_container)
     return ExpectedTrajectoryOutput(float(μ[0]), float(σ[0]), gx, sgx, gt, sgt, summary=summary)
+
+
+def generate_indices(num_nodes, max_depth):
+    """generate_indices (utils.jl:217-221): all num_nodes^max_depth index vectors (1-based), first position fastest."""
+    grids = np.meshgrid(*([np.arange(1, num_nodes + 1)] * max_depth), indexing="ij")
+    return [list(map(int, v)) for v in np.stack([g.ravel(order="F") for g in grids], axis=1)]
+
+
+def gausshermite(n):
+    """Nodes and weights of the n-point Gauss-Hermite rule (weight exp(-x^2)), what the reference's callers pass as
+    `nodes`, `weights` (observables.jl:54-72 uses the sqrt(2) / sqrt(pi) change of variables of that rule)."""
+    return np.polynomial.hermite.hermgauss(n)
+
+
+def simulate_trajectory_ghq(T, tp, *, inner_solve_xstarts, resolutions, nodes, weights, indices,
+                            spatial_gradients_container=None, hyperparameter_gradients_container=None,
+                            dual_directions=None, device=0):
+    """simulate_trajectory_ghq (rollout.jl:409-467) on the GPU: one trajectory per entry of `indices` (1-based index
+    vectors of length depth >= horizon + 1), driven by the GaussHermiteObservable (observables.jl:32-81,157)."""
+    d, h, M = len(tp.x0), tp.horizon, len(indices)
+    T.x0[:] = tp.x0  # set_start! (rollout.jl:422)
+    nodes = np.asarray(nodes, dtype=np.float64); weights = np.asarray(weights, dtype=np.float64)
+    idx = np.asarray(indices, dtype=np.int64) - 1  # M x depth
+    if idx.ndim != 2 or idx.min() < 0 or idx.max() >= len(nodes):
+        raise RboError("BoundsError: indices must be equal-length vectors of 1-based node indices")  # nodes[indices[i]]
+    if idx.shape[1] < h + 1:
+        raise RboError("AssertionError: Maximum invocations have been used")  # observables.jl:55
+    if len(resolutions) < M:
+        raise RboError("BoundsError: resolutions shorter than indices")
+    want_grad = spatial_gradients_container is not None and hyperparameter_gradients_container is not None
+    vals = np.zeros(M)
+    gx = np.zeros((d, M), order="F") if want_grad else None
+    gt = np.zeros((len(tp.θ), M), order="F") if want_grad else None
+    status = np.zeros(M, np.int32)
+    eng = RolloutEngine(device)
+    try:
+        eng.set_surrogate(T.fs)
+        eng.set_quadrature(nodes[idx].T, weights[idx].T)
+        eng.set_starts(inner_solve_xstarts)
+        if want_grad and dual_directions is None and h > 0:
+            dual_directions = np.asfortranarray(np.random.rand(d, h, M))
+        fmini = float(np.min(get_observations(T.s)))  # rollout.jl:109
+        summary = eng.rollout(tp.x0, tp.θ, tp.spatial_lbs, tp.spatial_ubs, h, fmini, vals, gx, gt,
+                              dual_dirs=dual_directions if want_grad else None, status=status, gauss_hermite=True)
+    finally:
+        eng.close()
+    bad = np.nonzero(status)[0]
+    if len(bad):
+        names = {1: "PosDefException (rbs.jl:412)", 2: "DomainError (rbs.jl:528)",
+                 4: "ArgumentError: reducing over an empty collection (rbf_optim.jl:97)", 5: "SingularException (rollout.jl:188)"}
+        raise RboError(f"sample {bad[0] + 1}: {names.get(int(status[bad[0]]), 'error')}")
+    resolutions[:M] = vals  # rollout.jl:444; entries past length(indices) are left as they were
+    μ, σ = _mean_std_rows(resolutions)  # rollout.jl:455-456 take the whole vector
+    if not want_grad:
+        return ExpectedTrajectoryOutput(float(μ[0]), float(σ[0]), summary=summary)
+    spatial_gradients_container[:, :M] = gx
+    hyperparameter_gradients_container[:, :M] = gt
+    mgx, sgx = _mean_std_rows(spatial_gradients_container)
+    mgt, sgt = _mean_std_rows(hyperparameter_gradients_container)
+    return ExpectedTrajectoryOutput(float(μ[0]), float(σ[0]), mgx, sgx, mgt, sgt, summary=summary)
 
 
 def multistart_base_solve(surrogate, xfinal, *, spatial_lbs, spatial_ubs, guesses, θfixed, device=0):

@@ -54,7 +54,9 @@ struct rbo_handle {
   int* work_counter = nullptr;
   double* sums = nullptr;
   int sums_len = 0;
-  double *dual_dirs = nullptr, *x_forced = nullptr, *cs_tape = nullptr;
+  double *dual_dirs = nullptr, *x_forced = nullptr, *cs_tape = nullptr, *gh_nodes = nullptr, *gh_weights = nullptr;
+  size_t cap_ghn = 0, cap_ghw = 0;
+  int gh_depth = 0, gh_M = 0;
   size_t dual_cap = 0, forced_cap = 0, tape_cap = 0;
   size_t cap_Xb = 0, cap_yb = 0, cap_c0 = 0, cap_u0 = 0, cap_Lf = 0, cap_Lb = 0, cap_rn = 0, cap_starts = 0;
   // last call
@@ -153,7 +155,7 @@ int rbo_destroy(rbo_handle* h) {
   cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->Xb, h->yb, h->c0, h->u0, h->Lf, h->Lb, h->rn, h->starts, h->sobol_dirs, h->values, h->grad_x, h->grad_theta, h->xs, h->ys,
                   h->gys, h->alphas, h->best_index, h->grad_case, h->status, h->n_evals, h->start_status, h->start_iters, h->work_counter, h->sums,
-                  h->dual_dirs, h->x_forced, h->cs_tape};
+                  h->dual_dirs, h->x_forced, h->cs_tape, h->gh_nodes, h->gh_weights};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -310,6 +312,20 @@ int rbo_get_normals(rbo_handle* h, double* out) {
   return RBO_SUCCESS;
 }
 
+int rbo_set_quadrature(rbo_handle* h, const double* nodes, const double* weights, int depth, int m_count) {
+  if (!h) return RBO_ERR_ARG;
+  if (!nodes || !weights || depth < 1 || m_count < 1) return fail(h, RBO_ERR_ARG, "rbo_set_quadrature: bad arguments");
+  CK(h, cudaSetDevice(h->device));
+  const size_t n = (size_t)depth * m_count;
+  CK(h, dev_reserve(&h->gh_nodes, &h->cap_ghn, n));
+  CK(h, dev_reserve(&h->gh_weights, &h->cap_ghw, n));
+  CK(h, cudaMemcpyAsync(h->gh_nodes, nodes, n * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->gh_weights, weights, n * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->gh_depth = depth; h->gh_M = m_count;
+  return RBO_SUCCESS;
+}
+
 int rbo_set_starts(rbo_handle* h, const double* starts, int S) {
   if (!h) return RBO_ERR_ARG;
   if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_set_starts: call rbo_set_surrogate first");
@@ -385,14 +401,16 @@ static double f_eval_exec(double n, double d) { return n * n * (d + 2) + n * (3 
 static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, int ntheta, const double* lbs, const double* ubs, int horizon,
                           double fmini, int mode, int flags, const double* dual_dirs_dev, const double* x_forced_dev, bool want_summary,
                           rbo_summary* summary) {
-  const bool myopic = (flags & RBO_FLAG_MYOPIC_INTERNAL) != 0;
+  const bool myopic = (flags & RBO_FLAG_MYOPIC_INTERNAL) != 0, ghq = (flags & RBO_FLAG_GAUSS_HERMITE) != 0;
   if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_rollout: no surrogate (rbo_set_surrogate)");
-  if (!h->rn && !myopic) return fail(h, RBO_ERR_STATE, "rbo_rollout: no normals (rbo_set_normals / rbo_generate_normals)");
+  if (ghq && !h->gh_nodes) return fail(h, RBO_ERR_STATE, "rbo_rollout: no quadrature data (rbo_set_quadrature)");
+  if (!h->rn && !myopic && !ghq) return fail(h, RBO_ERR_STATE, "rbo_rollout: no normals (rbo_set_normals / rbo_generate_normals)");
   if (!h->starts && !(flags & RBO_FLAG_TEACHER_FORCED)) return fail(h, RBO_ERR_STATE, "rbo_rollout: no starts (rbo_set_starts)");
   if (!x0 || !theta || !lbs || !ubs || ntheta < 1) return fail(h, RBO_ERR_ARG, "rbo_rollout: bad arguments");
   if (horizon < 0 || horizon + 1 > RBO_MAXFAN) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_rollout: horizon %d not in [0, %d]", horizon, RBO_MAXFAN - 1);
-  if (!myopic && horizon + 1 > h->hp1) return fail(h, RBO_ERR_ARG, "rbo_rollout: normals hold %d steps, horizon + 1 = %d needed", h->hp1, horizon + 1);
-  const int M = myopic ? 1 : h->M;
+  if (!myopic && !ghq && horizon + 1 > h->hp1) return fail(h, RBO_ERR_ARG, "rbo_rollout: normals hold %d steps, horizon + 1 = %d needed", h->hp1, horizon + 1);
+  if (ghq && horizon + 1 > h->gh_depth) return fail(h, RBO_ERR_ARG, "rbo_rollout: quadrature depth %d < horizon + 1 = %d", h->gh_depth, horizon + 1);
+  const int M = myopic ? 1 : (ghq ? h->gh_M : h->M);
   if ((flags & RBO_FLAG_TEACHER_FORCED) && !x_forced_dev) return fail(h, RBO_ERR_ARG, "rbo_rollout: teacher forcing without x_forced");
   if (mode != RBO_MODE_VALUE && mode != RBO_MODE_VALUE_GRAD) return fail(h, RBO_ERR_ARG, "rbo_rollout: bad mode");
   for (int a = 0; a < h->d; ++a)
@@ -414,6 +432,7 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   for (int a = 0; a < h->d; ++a) { P.x0[a] = x0[a]; P.lbs[a] = lbs[a]; P.ubs[a] = ubs[a]; }
   P.Xb = h->Xb; P.yb = h->yb; P.c0 = h->c0; P.u0 = h->u0; P.Lf = h->Lf; P.Lb = h->Lb; P.rn = h->rn; P.starts = h->starts;
   P.dual_dirs = dual_dirs_dev; P.x_forced = x_forced_dev;
+  P.gh_nodes = h->gh_nodes; P.gh_weights = h->gh_weights; P.gh_depth = h->gh_depth;
   P.values = h->values; P.grad_x = h->grad_x; P.grad_theta = h->grad_theta; P.best_index = h->best_index; P.grad_case = h->grad_case;
   P.status = h->status; P.xs = h->xs; P.ys = h->ys; P.gys = h->gys; P.alphas = h->alphas; P.n_evals = h->n_evals;
   P.start_status = h->tape_enabled ? h->start_status : nullptr; P.start_iters = h->tape_enabled ? h->start_iters : nullptr;
@@ -494,7 +513,8 @@ int rbo_rollout(rbo_handle* h, const double* x0, const double* theta, int ntheta
   if (!values) return fail(h, RBO_ERR_ARG, "rbo_rollout: values is NULL");
   if (mode == RBO_MODE_VALUE_GRAD && (!grad_x || !grad_theta)) return fail(h, RBO_ERR_ARG, "rbo_rollout: gradient containers missing in VALUE_GRAD mode");
   CK(h, cudaSetDevice(h->device));
-  const size_t nd = (size_t)h->M * std::max(horizon, 0) * h->d;
+  const size_t Mrun = (flags & RBO_FLAG_GAUSS_HERMITE) ? (size_t)h->gh_M : (size_t)h->M;
+  const size_t nd = Mrun * std::max(horizon, 0) * h->d;
   int rc = upload_opt(h, (mode == RBO_MODE_VALUE_GRAD) ? dual_dirs : nullptr, nd, &h->dual_dirs, &h->dual_cap);
   if (rc) return rc;
   rc = upload_opt(h, (flags & RBO_FLAG_TEACHER_FORCED) ? x_forced : nullptr, nd, &h->x_forced, &h->forced_cap);
@@ -503,7 +523,7 @@ int rbo_rollout(rbo_handle* h, const double* x0, const double* theta, int ntheta
   rc = launch_rollout(h, x0, theta, ntheta, lbs, ubs, horizon, fmini, mode, flags, (mode == RBO_MODE_VALUE_GRAD && dual_dirs) ? h->dual_dirs : nullptr,
                       (flags & RBO_FLAG_TEACHER_FORCED) ? h->x_forced : nullptr, true, summary ? summary : &local);
   if (rc) return rc;
-  const size_t M = h->M;
+  const size_t M = Mrun;
   CK(h, cudaMemcpyAsync(values, h->values, M * 8, cudaMemcpyDeviceToHost, h->stream));
   if (mode == RBO_MODE_VALUE_GRAD) {
     CK(h, cudaMemcpyAsync(grad_x, h->grad_x, M * h->d * 8, cudaMemcpyDeviceToHost, h->stream));

@@ -35,6 +35,9 @@ struct DevProblem {
   const double* starts;  // [S][d]
   const double* dual_dirs;  // [M][h][d] or nullptr
   const double* x_forced;   // [M][h][d] or nullptr
+  const double* gh_nodes;   // [M][gh_depth] Gauss-Hermite nodes per sample and step (RBO_FLAG_GAUSS_HERMITE)
+  const double* gh_weights; // [M][gh_depth]
+  int gh_depth;
   // outputs (device)
   double* values;      // [M]
   double* grad_x;      // [M][d]
@@ -94,7 +97,7 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.ppost1 = take(RSmax * W * q1);
   p.phess = take(RSmax * W * 2 * (T2 + 1));
   p.bestx = take(d);
-  p.misc = take(64 + 2 * q1 * q1);
+  p.misc = take(64 + 2 * q1 * q1 + 2 * q1);
   p.adj = take(19 * d + 32);
   p.pairs = take((5 * (W + 2) + 1) / 2);  // product items
   p.tbl = take((T2 + 2) / 2 + 1);

@@ -965,6 +965,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
             const int p = e / q1, q = e - p * q1;
             const double dk = (p == q) ? (p == 0 ? P.k0 : -P.d2k0) : 0.0;  // eval_Dk(kernel, 0) rbf.jl:152-159
             if (p <= q) { Sg[p * q1 + q] = dk - acc; Sg[q * q1 + p] = dk - acc; }  // Symmetric(...) takes the upper triangle
+            if (p == 0) misc[8 + q1 * q1 + q1 + q] = acc;  // [|v0|^2, V_q.v0]: sigma and grad sigma of the Gauss-Hermite observable
             if (e == 0) misc[4] = acc;  // |l|^2
           } else misc[5] = acc;         // l . u
         }
@@ -977,14 +978,25 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
         if (tid == 0) {
           const int r = k.nf;  // index of the new fantasy row
           const double* dmu = misc + 8 + q1 * q1;
-          bool pd = chol_inplace(Sg, q1, q1);
-          if (!pd && si[I_TSTATUS] == RBO_TRAJ_OK) si[I_TSTATUS] = RBO_TRAJ_NOT_PD_JOINT;
-          const double* rnm = P.rn + (size_t)m + (size_t)P.M * q1 * step;
-          double yv = dmu[0] + Sg[0] * __ldg(rnm);
-          for (int a = 0; a < d; ++a) {
-            double v = dmu[1 + a];
-            for (int j = 0; j <= a + 1; ++j) v += Sg[(a + 1) * q1 + j] * __ldg(rnm + (size_t)P.M * j);
-            k.gyf[r * d + a] = v;
+          double yv;
+          if (P.flags & RBO_FLAG_GAUSS_HERMITE) {
+            // GaussHermiteObservable functor (observables.jl:54-64): y = mu + sqrt(2) sigma node, grad y = grad mu + sqrt(2) grad sigma node
+            const double* raw = misc + 8 + q1 * q1 + q1;
+            const double var = P.k0 - raw[0];  // rbs.jl:528
+            if (!(var >= 0.0) && si[I_TSTATUS] == RBO_TRAJ_OK) si[I_TSTATUS] = RBO_TRAJ_NEG_VARIANCE;
+            const double sigma = sqrt(var), node = __ldg(P.gh_nodes + (size_t)m * P.gh_depth + step), s2n = 1.4142135623730951 * node;
+            yv = dmu[0] + s2n * sigma;
+            for (int a = 0; a < d; ++a) k.gyf[r * d + a] = dmu[1 + a] + s2n * (-raw[1 + a] / sigma);  // rbs.jl:529
+          } else {
+            bool pd = chol_inplace(Sg, q1, q1);
+            if (!pd && si[I_TSTATUS] == RBO_TRAJ_OK) si[I_TSTATUS] = RBO_TRAJ_NOT_PD_JOINT;
+            const double* rnm = P.rn + (size_t)m + (size_t)P.M * q1 * step;
+            yv = dmu[0] + Sg[0] * __ldg(rnm);
+            for (int a = 0; a < d; ++a) {
+              double v = dmu[1 + a];
+              for (int j = 0; j <= a + 1; ++j) v += Sg[(a + 1) * q1 + j] * __ldg(rnm + (size_t)P.M * j);
+              k.gyf[r * d + a] = v;
+            }
           }
           k.yf[r] = yv;
           for (int a = 0; a < d; ++a) k.Xf[r * d + a] = bestx[a];
@@ -1030,7 +1042,15 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
       double best = k.yf[0];
       int t = 0;
       for (int j = 1; j <= h; ++j) if (k.yf[j] < best) { best = k.yf[j]; t = j; }  // findmin: first minimum (rollout.jl:77-82)
-      P.values[m] = fmax(P.fmini - best, 0.0);
+      double val = fmax(P.fmini - best, 0.0);
+      if (P.flags & RBO_FLAG_GAUSS_HERMITE) {
+        // resolve(gho; fmini) (observables.jl:66-72); get_gradient(gho; at) = weights[at] * gradients[:, at] (observables.jl:157)
+        const double* wq = P.gh_weights + (size_t)m * P.gh_depth;
+        val = __ldg(wq + t) * val / 1.7724538509055159;
+        for (int j = 0; j <= h; ++j)
+          for (int a = 0; a < d; ++a) k.gyf[j * d + a] *= __ldg(wq + j);
+      }
+      P.values[m] = val;
       si[I_T] = t;
       int tc = 0;
       if (P.mode == RBO_MODE_VALUE_GRAD) tc = (P.fmini <= best) ? 1 : (t == 0 ? 2 : 3);  // rollout.jl:241-251
@@ -1038,6 +1058,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
       if (P.best_index) P.best_index[m] = t;
       if (P.grad_case) P.grad_case[m] = tc;
     }
+    __syncthreads();
     if (P.xs) for (int i = tid; i < (h + 1) * d; i += RBO_THREADS) P.xs[(size_t)m * (h + 1) * d + i] = k.Xf[i];
     if (P.gys) for (int i = tid; i < (h + 1) * d; i += RBO_THREADS) P.gys[(size_t)m * (h + 1) * d + i] = k.gyf[i];
     if (P.ys) for (int i = tid; i <= h; i += RBO_THREADS) P.ys[(size_t)m * (h + 1) + i] = k.yf[i];

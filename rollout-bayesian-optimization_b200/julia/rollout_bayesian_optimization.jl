@@ -144,6 +144,49 @@ function simulate_trajectory_mc(T::Trajectory, tp::TrajectoryParameters, observa
     return _rbo_simulate(T, tp, inner_solve_xstarts, resolutions, spatial_gradients_container, hyperparameter_gradients_container)
 end
 
+# simulate_trajectory_ghq (rollout.jl:409-467): one trajectory per entry of `indices`, GaussHermiteObservable draws
+function simulate_trajectory_ghq(T::Trajectory, tp::TrajectoryParameters;
+        inner_solve_xstarts::Matrix{T1}, resolutions::Vector{T1}, nodes::Vector{T1}, weights::Vector{T1}, indices,
+        spatial_gradients_container::Union{Nothing, Matrix{T1}} = nothing,
+        hyperparameter_gradients_container::Union{Nothing, Matrix{T1}} = nothing) where T1 <: Real
+    h = _rbo_handle()
+    fs = get_fantasy_surrogate(T)
+    set_start!(T, get_starting_point(tp))                                   # rollout.jl:422
+    N = get_known_observations(fs)
+    _rbo_set_surrogate!(h, fs.X, fs.L.data, fs.y, fs.cs[1], N, fs.ψ, fs.g, fs.σn2)
+    depth, M, d, hor = length(first(indices)), length(indices), length(tp.x0), tp.horizon
+    depth >= hor + 1 || error("AssertionError: Maximum invocations have been used")          # observables.jl:55
+    nd = Matrix{Float64}(undef, depth, M); wt = similar(nd)
+    for (m, idx) in enumerate(vec(indices))                                 # rollout.jl:431-432
+        nd[:, m] = nodes[idx]; wt[:, m] = weights[idx]
+    end
+    _rbo_check(h, ccall((:rbo_set_quadrature, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Cint), h.ptr, nd, wt, depth, M))
+    _rbo_check(h, ccall((:rbo_set_starts, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), h.ptr, inner_solve_xstarts, size(inner_solve_xstarts, 2)))
+    want_grad = !isnothing(spatial_gradients_container) && !isnothing(hyperparameter_gradients_container)
+    dual = want_grad ? rand(d, max(hor, 1), M) : zeros(0)
+    fmini = minimum(get_observations(get_base_surrogate(T)))
+    vals = zeros(M); gx = zeros(d, M); gθ = zeros(length(tp.θ), M)
+    status = zeros(Int32, M); summary = RboSummary(); θ = Vector{Float64}(tp.θ)
+    _rbo_check(h, ccall((:rbo_rollout, librbo), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint, Cint, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{RboSummary}),
+        h.ptr, tp.x0, θ, length(θ), tp.spatial_lbs, tp.spatial_ubs, hor, fmini, want_grad ? 1 : 0, 2 #= RBO_FLAG_GAUSS_HERMITE =#,
+        want_grad ? dual : C_NULL, C_NULL, vals, want_grad ? gx : C_NULL, want_grad ? gθ : C_NULL, C_NULL, C_NULL, status, summary))
+    bad = findfirst(!=(0), status)
+    isnothing(bad) || error("sample $bad: " * get(_RBO_STATUS, Int(status[bad]), "error"))
+    resolutions[1:M] = vals                                                 # rollout.jl:444
+    μxθ = Distributions.mean(resolutions)                                  # rollout.jl:455-456: the whole vector
+    σ_μxθ = Distributions.std(resolutions, mean = μxθ)
+    want_grad || return ExpectedTrajectoryOutput(μxθ = μxθ, σ_μxθ = σ_μxθ)
+    spatial_gradients_container[:, 1:M] = gx
+    hyperparameter_gradients_container[:, 1:M] = gθ
+    ∇μx = vec(Distributions.mean(spatial_gradients_container, dims = 2))
+    σ_∇μx = vec(Distributions.std(spatial_gradients_container, dims = 2, mean = ∇μx))
+    ∇μθ = vec(Distributions.mean(hyperparameter_gradients_container, dims = 2))
+    σ_∇μθ = vec(Distributions.std(hyperparameter_gradients_container, dims = 2, mean = ∇μθ))
+    return ExpectedTrajectoryOutput(μxθ = μxθ, σ_μxθ = σ_μxθ, ∇μx = ∇μx, σ_∇μx = σ_∇μx, ∇μθ = ∇μθ, σ_∇μθ = σ_∇μθ)
+end
+
 function multistart_base_solve!(surrogate::Surrogate, xfinal::Vector{T};
         spatial_lbs::Vector{T}, spatial_ubs::Vector{T}, guesses::Matrix{T}, θfixed::Vector{T}) where T <: Real
     if get_name(get_decision_rule(surrogate)) == "Random"                 # rbf_optim.jl:111-114 stays on the host RNG

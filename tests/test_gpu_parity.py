@@ -318,3 +318,73 @@ def test_sga_loop_matches_oracle_driven_loop(pkg, orc):
         assert np.max(np.abs(hist[it][2] - g)) <= 1e-5 * max(1.0, np.abs(g).max())
         pkg.update_optimizer(opt, x, g)
     assert relerr(xg, x) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# Gauss-Hermite estimator: simulate_trajectory_ghq (rollout.jl:409-467)
+# ---------------------------------------------------------------------------------------------------
+def gh_case(pkg, orc, name, n_nodes, **kw):
+    wl = pkg.problems.make_workload(name, M=n_nodes ** (kw["h"] + 1), **kw)
+    sur = wl.surrogate()
+    nodes, weights = pkg.gausshermite(n_nodes)
+    indices = pkg.generate_indices(n_nodes, wl.h + 1)
+    idx = np.asarray(indices) - 1
+    starts = orc.generate_initial_guesses(wl.S, wl.lbs, wl.ubs)
+    dd = np.asfortranarray(np.random.default_rng(11).random((wl.d, max(wl.h, 1), wl.M)))
+    rn0 = np.zeros((wl.M, wl.d + 1, wl.h + 1), order="F")
+    P = oracle_problem(orc, wl, sur, rn0, starts, 1, dual_dirs=dd, gh_nodes=np.asfortranarray(nodes[idx].T),
+                       gh_weights=np.asfortranarray(weights[idx].T))
+    return wl, sur, nodes, weights, indices, idx, starts, dd, P
+
+
+@pytest.mark.parametrize("name,n_nodes,kw", [("C2", 4, dict(N=14, h=2, S=5)), ("GP:2:0.25", 3, dict(N=12, h=3, S=4))])
+def test_gauss_hermite_teacher_forced_parity(pkg, orc, name, n_nodes, kw):
+    wl, sur, nodes, weights, indices, idx, starts, dd, P = gh_case(pkg, orc, name, n_nodes, **kw)
+    ref = P.rollout()
+    eng = pkg.RolloutEngine(0)
+    try:
+        eng.set_surrogate(pkg.FantasySurrogate(sur, wl.h))
+        eng.set_quadrature(nodes[idx].T, weights[idx].T)
+        eng.set_starts(starts)
+        M = wl.M
+        vals, gx, gt = np.zeros(M), np.zeros((wl.d, M), order="F"), np.zeros((1, M), order="F")
+        bi, gc, st = np.zeros(M, np.int32), np.zeros(M, np.int32), np.zeros(M, np.int32)
+        eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), vals, gx, gt, dual_dirs=dd,
+                    x_forced=np.asfortranarray(ref["xs"][:, 1:, :]), best_index=bi, grad_case=gc, status=st, gauss_hermite=True)
+        tape = eng.tape(wl.h)
+    finally:
+        eng.close()
+    assert np.array_equal(st, ref["status"]) and np.array_equal(bi, ref["best_index"]) and np.array_equal(gc, ref["grad_case"])
+    assert relerr(tape["ys"], ref["ys"]) < 1e-9 and relerr(tape["gys"], ref["gys"]) < 1e-8
+    assert relerr(vals, ref["values"], floor=np.abs(ref["values"]).max()) < 1e-9
+    gscale = np.maximum(np.abs(ref["grad_x"]).max(axis=0, keepdims=True), 1e-9)
+    assert np.max(np.abs(gx - ref["grad_x"]) / gscale) < 1e-6
+    assert np.max(np.abs(gt - ref["grad_theta"]) / np.maximum(np.abs(ref["grad_theta"]), 1e-9)) < 1e-6
+    assert (ref["grad_case"] == 3).sum() > 0
+
+
+def test_simulate_trajectory_ghq_free_running(pkg, orc):
+    """The reference-named entry point against the oracle's own free-running Gauss-Hermite rollout."""
+    wl, sur, nodes, weights, indices, idx, starts, dd, P = gh_case(pkg, orc, "C2", 5, N=14, h=2, S=6)
+    ref = P.rollout()
+    fs = pkg.FantasySurrogate(sur, wl.h)
+    T = pkg.Trajectory(sur, fs, start=wl.x0, hypers=wl.theta, horizon=wl.h)
+    tp = pkg.TrajectoryParameters(wl.x0, wl.theta, wl.h, wl.M, True, wl.lbs, wl.ubs)
+    res, gxc, gtc = np.zeros(wl.M), np.zeros((wl.d, wl.M), order="F"), np.zeros((1, wl.M), order="F")
+    eto = pkg.simulate_trajectory_ghq(T, tp, inner_solve_xstarts=starts, resolutions=res, nodes=nodes, weights=weights,
+                                      indices=indices, spatial_gradients_container=gxc, hyperparameter_gradients_container=gtc,
+                                      dual_directions=dd)
+    vscale = np.abs(ref["values"]).max()
+    assert np.mean(np.abs(res - ref["values"]) <= 1e-8 * vscale) >= 0.97
+    gscale = np.maximum(np.abs(ref["grad_x"]).max(axis=0, keepdims=True), 1e-9 * max(np.abs(ref["grad_x"]).max(), 1e-300))
+    gerr = np.max(np.abs(gxc - ref["grad_x"]) / gscale, axis=0)
+    assert np.mean(gerr <= 1e-5) >= 0.95
+    assert abs(pkg.mean(eto) - ref["values"].mean()) <= 1e-6 * vscale + 0.02 * ref["values"].std()
+    assert np.isclose(pkg.std(eto), res.std(ddof=1), rtol=1e-12)
+    # value-only call: gradient containers omitted (rollout.jl:458-459)
+    res2 = np.zeros(wl.M)
+    eto2 = pkg.simulate_trajectory_ghq(T, tp, inner_solve_xstarts=starts, resolutions=res2, nodes=nodes, weights=weights, indices=indices)
+    assert np.allclose(res2, res, rtol=1e-12, atol=1e-300) and eto2.grad_μx is None
+    with pytest.raises(pkg.RboError):  # depth < horizon + 1 (observables.jl:55 assertion)
+        pkg.simulate_trajectory_ghq(T, tp, inner_solve_xstarts=starts, resolutions=res2, nodes=nodes, weights=weights,
+                                    indices=pkg.generate_indices(5, wl.h))

@@ -200,3 +200,68 @@ def test_mean_std_matches_numpy(orc):
     v = np.random.default_rng(1).random(1000)
     m, s = orc.mean_std(v)
     assert np.isclose(m, v.mean(), rtol=1e-14) and np.isclose(s, v.std(ddof=1), rtol=1e-12)
+
+
+def gh_inputs(pkg, n_nodes, depth):
+    """nodes[indices[m]] / weights[indices[m]] of rollout.jl:431-432 as (depth x M) arrays."""
+    nodes, weights = pkg.gausshermite(n_nodes)
+    idx = np.asarray(pkg.generate_indices(n_nodes, depth)) - 1
+    return np.asfortranarray(nodes[idx].T), np.asfortranarray(weights[idx].T)
+
+
+def test_generate_indices_order(pkg):
+    # utils.jl:217-221: collect(product(1:n, 1:n, ...)) runs the FIRST position fastest
+    idx = pkg.generate_indices(3, 2)
+    assert idx[:4] == [[1, 1], [2, 1], [3, 1], [1, 2]] and len(idx) == 9 and idx[-1] == [3, 3]
+
+
+def test_gauss_hermite_horizon0_is_expected_improvement(pkg, orc):
+    """h = 0: sum_m w_m max(fmini - (mu + sqrt2 sigma z_m), 0) / sqrt(pi) is the n-point Gauss-Hermite estimate of
+    E[max(fmini - y, 0)], y ~ N(mu, sigma^2) = EI with xi = 0 (observables.jl:54-72); the sample gradients
+    (observables.jl:157, no 1/sqrt(pi) -- the later definition wins) sum to sqrt(pi) grad EI."""
+    n = 96
+    wl = pkg.problems.make_workload("C2", M=n, N=14, h=0, S=4, seed=3)
+    sur = wl.surrogate()
+    nodes, weights = gh_inputs(pkg, n, 1)
+    rn = np.zeros((n, wl.d + 1, 1), order="F")
+    starts = orc.generate_initial_guesses(4, wl.lbs, wl.ubs)
+    P = oracle_problem(orc, wl, sur, rn, starts, 1, gh_nodes=nodes, gh_weights=weights)
+    r = P.rollout()
+    e = P.eval_point(wl.x0, np.zeros((wl.d, 0), order="F"), np.zeros(0))
+    assert np.all(r["status"] == 0)
+    # the kink of max(., 0) limits Gauss-Hermite to ~1/n accuracy
+    assert abs(r["values"].sum() - e["alpha"]) <= 2e-2 * abs(e["alpha"])
+    assert set(np.unique(r["grad_case"])) <= {1, 2}
+    # the sample gradients are the exact derivative of the finite quadrature sum (away from its kinks)
+    x0, step, fd = wl.x0.copy(), 1e-6, np.zeros(wl.d)
+    for a in range(wl.d):
+        vals = []
+        for sgn in (1, -1):
+            wl.x0 = x0.copy(); wl.x0[a] += sgn * step
+            vals.append(oracle_problem(orc, wl, sur, rn, starts, 0, gh_nodes=nodes, gh_weights=weights).rollout()["values"].sum())
+        fd[a] = (vals[0] - vals[1]) / (2 * step)
+    wl.x0 = x0
+    assert np.allclose(r["grad_x"].sum(axis=1) / np.sqrt(np.pi), fd, rtol=1e-6, atol=1e-9)
+
+
+def test_gauss_hermite_observable_formula(pkg, orc):
+    """Teacher-forced GH rollout: y_k = mu_k(x_k) + sqrt(2) sigma_k(x_k) node_k re-derived with eval_point on the
+    surrogate extended by the earlier fantasy points; value = w[t] max(fmini - min y, 0) / sqrt(pi)."""
+    wl = pkg.problems.make_workload("C2", M=9, N=14, h=1, S=4, seed=3)
+    sur = wl.surrogate()
+    nodes, weights = gh_inputs(pkg, 3, 2)
+    rn = np.zeros((9, wl.d + 1, 2), order="F")
+    starts = orc.generate_initial_guesses(4, wl.lbs, wl.ubs)
+    P = oracle_problem(orc, wl, sur, rn, starts, 1, gh_nodes=nodes, gh_weights=weights)
+    r = P.rollout()
+    fmini = float(np.min(sur.y))
+    for m in range(9):
+        ys = []
+        for k in range(2):
+            e = P.eval_point(r["xs"][:, k, m], np.asfortranarray(r["xs"][:, :k, m]), np.asarray(ys))
+            ys.append(e["mu"] + np.sqrt(2) * e["sigma"] * nodes[k, m])
+            assert np.isclose(ys[-1], r["ys"][k, m], rtol=1e-10, atol=1e-12)
+            gy = (e["dmu"] + np.sqrt(2) * e["dsigma"] * nodes[k, m]) * weights[k, m]
+            assert np.allclose(gy, r["gys"][:, k, m], rtol=1e-9, atol=1e-12)
+        t = int(np.argmin(ys))
+        assert np.isclose(r["values"][m], weights[t, m] * max(fmini - min(ys), 0.0) / np.sqrt(np.pi), rtol=1e-12, atol=1e-15)
