@@ -40,7 +40,7 @@ struct rbo_handle {
   KernelSpec kern;
   int rule_id = 0;
   double sigma_tol = 1e-8, sigma_n2 = 1e-6, k0 = 1, d2k0 = 0, ymin_base = 0;
-  double *Xb = nullptr, *yb = nullptr, *c0 = nullptr, *u0 = nullptr, *Lf = nullptr, *Lb = nullptr;
+  double *Xb = nullptr, *yb = nullptr, *c0 = nullptr, *u0 = nullptr, *Lf = nullptr, *Lb = nullptr, *Lbf = nullptr;
   // normals / starts
   int M = 0, hp1 = 0;
   double* rn = nullptr;
@@ -58,7 +58,7 @@ struct rbo_handle {
   size_t cap_ghn = 0, cap_ghw = 0;
   int gh_depth = 0, gh_M = 0;
   size_t dual_cap = 0, forced_cap = 0, tape_cap = 0;
-  size_t cap_Xb = 0, cap_yb = 0, cap_c0 = 0, cap_u0 = 0, cap_Lf = 0, cap_Lb = 0, cap_rn = 0, cap_starts = 0;
+  size_t cap_Xb = 0, cap_yb = 0, cap_c0 = 0, cap_u0 = 0, cap_Lf = 0, cap_Lb = 0, cap_Lbf = 0, cap_rn = 0, cap_starts = 0;
   // last call
   int last_h = 0, last_mode = 0, last_nth = 1;
   bool tape_enabled = true;
@@ -153,7 +153,7 @@ int rbo_destroy(rbo_handle* h) {
   if (!h) return RBO_SUCCESS;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->Xb, h->yb, h->c0, h->u0, h->Lf, h->Lb, h->rn, h->starts, h->sobol_dirs, h->values, h->grad_x, h->grad_theta, h->xs, h->ys,
+  void* ptrs[] = {h->Xb, h->yb, h->c0, h->u0, h->Lf, h->Lb, h->Lbf, h->rn, h->starts, h->sobol_dirs, h->values, h->grad_x, h->grad_theta, h->xs, h->ys,
                   h->gys, h->alphas, h->best_index, h->grad_case, h->status, h->n_evals, h->start_status, h->start_iters, h->work_counter, h->sums,
                   h->dual_dirs, h->x_forced, h->cs_tape, h->gh_nodes, h->gh_weights};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -215,45 +215,61 @@ int rbo_set_surrogate(rbo_handle* h, int d, int N, const double* X, int ldX, con
     for (int k = 0; k < i; ++k) s -= Lij(i, k) * u0[k];
     u0[i] = s / Lij(i, i);
   }
-  // forward / backward 32-row panels, k-major with pitch RBO_LP (Dinv_ib = inverse of the 32x32 diagonal block):
-  //   forward  panel ib: k = 0 .. 32 ib - 1 : -(Dinv_ib L[32 ib .., k])[r]          ; then kk = 0..31 : Dinv_ib[r][kk]
-  //   backward panel ib: k' = 0 .. N32 - 32 (ib+1) - 1 : -(Dinv_ib' L[32 (ib+1) + k', 32 ib ..]')[r] ; then kk : Dinv_ib[kk][r]
+  // Explicit inverse of the base factor, in extended precision (one rounding per stored entry): every later
+  // "triangular solve" against L0 is then a dependency-free panel product on the FP64 tensor cores.
   const int BR = RBO_BR, LP = RBO_LP, nb32 = (N + BR - 1) / BR, N32 = nb32 * BR;
   h->nb32 = nb32;
+  std::vector<long double> Lr((size_t)N32 * N32, 0.0L), Li((size_t)N32 * N32, 0.0L);  // row-major L0 and L0^-1 (identity on the padding)
+  for (int i = 0; i < N32; ++i)
+    for (int k = 0; k <= i; ++k) Lr[(size_t)i * N32 + k] = Lij(i, k);
+  for (int i = 0; i < N32; ++i) {  // row i of the inverse: Li[i][:] = (e_i - sum_{k<i} L[i][k] Li[k][:]) / L[i][i]
+    long double* ri = Li.data() + (size_t)i * N32;
+    const long double* li = Lr.data() + (size_t)i * N32;
+    for (int k = 0; k < i; ++k) {
+      const long double lik = li[k];
+      if (lik == 0.0L) continue;
+      const long double* rk = Li.data() + (size_t)k * N32;
+      for (int j = 0; j <= k; ++j) ri[j] -= lik * rk[j];
+    }
+    ri[i] += 1.0L;
+    const long double dinv = 1.0L / li[i];
+    for (int j = 0; j <= i; ++j) ri[j] *= dinv;
+  }
+  auto Linv = [&](int i, int j) -> double { return (double)Li[(size_t)i * N32 + j]; };
+  // forward / backward 32-row panels of L0^-1, k-major with pitch RBO_LP, cut into 32-k chunks:
+  //   forward  panel ib (rows r0 = 32 ib ..): k = 0 .. r0 + 31                : Linv[r0 + r][k]        (v_I = sum_{J<=I} Linv[I][J] b_J)
+  //   backward panel ib: kk = 0 .. N32 - r0 - 33 : Linv[r0 + 32 + kk][r0 + r] ; then kk = 0..31 : Linv[r0 + kk][r0 + r]
+  //                                                                                                   (w_I = sum_{J>=I} Linv[J][I]' b_J)
   const size_t nLf = (size_t)LP * BR * ((size_t)nb32 * (nb32 + 1) / 2), nLb = nLf;
   std::vector<double> Lf(nLf, 0.0), Lb(nLb, 0.0);
-  std::vector<double> Dinv((size_t)BR * BR);
   for (int ib = 0; ib < nb32; ++ib) {
     const int r0 = BR * ib;
-    for (int cc = 0; cc < BR; ++cc)
-      for (int rr = 0; rr < BR; ++rr) {
-        double t = (rr == cc) ? 1.0 : 0.0;
-        for (int j = cc; j < rr; ++j) t -= Lij(r0 + rr, r0 + j) * Dinv[(size_t)j * BR + cc];
-        Dinv[(size_t)rr * BR + cc] = (rr < cc) ? 0.0 : t / Lij(r0 + rr, r0 + rr);
-      }
-    // The off-diagonal chunks are stored pre-multiplied by the inverted diagonal block and negated, so that a panel is one
-    // accumulation:  v_I = Dinv b_I - (Dinv L_{I,<I}) v_{<I}   (forward),   w_I = Dinv' b_I - (Dinv' L_{>I,I}') w_{>I}   (backward)
     double* pf = Lf.data() + (size_t)LP * BR * ((size_t)ib * (ib + 1) / 2);
-    const int nk = BR * ib;
-    for (int k = 0; k < nk; ++k)
-      for (int r = 0; r < BR; ++r) {
-        double acc = 0.0;
-        for (int j = 0; j <= r; ++j) acc += Dinv[(size_t)r * BR + j] * ((r0 + j < N) ? Lij(r0 + j, k) : 0.0);
-        pf[(size_t)k * LP + r] = -acc;
-      }
-    for (int kk = 0; kk < BR; ++kk)
-      for (int r = 0; r < BR; ++r) pf[(size_t)(nk + kk) * LP + r] = Dinv[(size_t)r * BR + kk];
+    for (int k = 0; k < r0 + BR; ++k)
+      for (int r = 0; r < BR; ++r) pf[(size_t)k * LP + r] = (k <= r0 + r) ? Linv(r0 + r, k) : 0.0;
     double* pb = Lb.data() + (size_t)LP * BR * ((size_t)nb32 * ib - (size_t)ib * (ib - 1) / 2);
-    const int k0 = BR * (ib + 1), nkb = N32 - k0;
+    const int k0 = r0 + BR, nkb = N32 - k0;
     for (int kk = 0; kk < nkb; ++kk)
-      for (int r = 0; r < BR; ++r) {
-        double acc = 0.0;  // (Dinv' M)[r][kk] with M[j][kk] = L[k0 + kk][r0 + j], Dinv'[r][j] = Dinv[j][r] (j >= r)
-        if (k0 + kk < N)
-          for (int j = r; j < BR; ++j) acc += Dinv[(size_t)j * BR + r] * ((r0 + j < N) ? Lij(k0 + kk, r0 + j) : 0.0);
-        pb[(size_t)kk * LP + r] = -acc;
-      }
+      for (int r = 0; r < BR; ++r) pb[(size_t)kk * LP + r] = Linv(k0 + kk, r0 + r);
     for (int kk = 0; kk < BR; ++kk)
-      for (int r = 0; r < BR; ++r) pb[(size_t)(nkb + kk) * LP + r] = Dinv[(size_t)kk * BR + r];
+      for (int r = 0; r < BR; ++r) pb[(size_t)(nkb + kk) * LP + r] = (kk >= r) ? Linv(r0 + kk, r0 + r) : 0.0;
+  }
+  // The backward panels once more in mma.m8n8k4 A-fragment order, for the pass that reads them straight from L2 (no staging):
+  // chunk (same order as Lb) -> 4 row-quarter tiles of 8 rows x 32 k -> 4 k-pairs -> lane (g = row, tg) -> {k = 8 p + tg, 8 p + 4 + tg}
+  const size_t nLbf = (size_t)1024 * ((size_t)nb32 * (nb32 + 1) / 2);
+  std::vector<double> Lbf(nLbf, 0.0);
+  for (int ib = 0; ib < nb32; ++ib) {
+    const int nc = nb32 - ib;
+    const double* pb = Lb.data() + (size_t)LP * BR * ((size_t)nb32 * ib - (size_t)ib * (ib - 1) / 2);
+    double* pf = Lbf.data() + (size_t)1024 * ((size_t)nb32 * ib - (size_t)ib * (ib - 1) / 2);
+    for (int cc = 0; cc < nc; ++cc)
+      for (int rq = 0; rq < 4; ++rq)
+        for (int pp = 0; pp < 4; ++pp)
+          for (int ln = 0; ln < 32; ++ln)
+            for (int e = 0; e < 2; ++e) {
+              const int g = ln >> 2, tg = ln & 3, k = cc * BR + 8 * pp + 4 * e + tg;
+              pf[(((size_t)cc * 4 + rq) * 4 + pp) * 64 + 2 * ln + e] = pb[(size_t)k * LP + 8 * rq + g];
+            }
   }
   CK(h, dev_reserve(&h->Xb, &h->cap_Xb, Xb.size()));
   CK(h, dev_reserve(&h->yb, &h->cap_yb, (size_t)N));
@@ -261,12 +277,14 @@ int rbo_set_surrogate(rbo_handle* h, int d, int N, const double* X, int ldX, con
   CK(h, dev_reserve(&h->u0, &h->cap_u0, (size_t)N8));
   CK(h, dev_reserve(&h->Lf, &h->cap_Lf, nLf));
   CK(h, dev_reserve(&h->Lb, &h->cap_Lb, nLb));
+  CK(h, dev_reserve(&h->Lbf, &h->cap_Lbf, nLbf));
   CK(h, cudaMemcpyAsync(h->Xb, Xb.data(), Xb.size() * 8, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->yb, y, (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->c0, c0.data(), (size_t)N8 * 8, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->u0, u0.data(), (size_t)N8 * 8, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->Lf, Lf.data(), nLf * 8, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->Lb, Lb.data(), nLb * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->Lbf, Lbf.data(), nLbf * 8, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));  // the staging vectors die here
   h->have_sur = true;
   return RBO_SUCCESS;
@@ -430,7 +448,7 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   P.kern = h->kern; P.rule_id = h->rule_id; P.sigma_tol = h->sigma_tol; P.sigma_n2 = h->sigma_n2; P.k0 = h->k0; P.d2k0 = h->d2k0;
   P.ymin_base = h->ymin_base; P.m52_c = std::sqrt(5.0) / h->kern.th[0]; P.fmini = fmini; P.theta1 = theta[0]; P.htol = h->htol; P.so = h->so;
   for (int a = 0; a < h->d; ++a) { P.x0[a] = x0[a]; P.lbs[a] = lbs[a]; P.ubs[a] = ubs[a]; }
-  P.Xb = h->Xb; P.yb = h->yb; P.c0 = h->c0; P.u0 = h->u0; P.Lf = h->Lf; P.Lb = h->Lb; P.rn = h->rn; P.starts = h->starts;
+  P.Xb = h->Xb; P.yb = h->yb; P.c0 = h->c0; P.u0 = h->u0; P.Lf = h->Lf; P.Lb = h->Lb; P.Lbf = h->Lbf; P.rn = h->rn; P.starts = h->starts;
   P.dual_dirs = dual_dirs_dev; P.x_forced = x_forced_dev;
   P.gh_nodes = h->gh_nodes; P.gh_weights = h->gh_weights; P.gh_depth = h->gh_depth;
   P.values = h->values; P.grad_x = h->grad_x; P.grad_theta = h->grad_theta; P.best_index = h->best_index; P.grad_case = h->grad_case;

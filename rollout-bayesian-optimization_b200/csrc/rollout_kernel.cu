@@ -25,11 +25,16 @@ namespace rbo {
 
 #ifdef RBO_PHASE_TIMERS
 __device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned long long g_aux_cycles[16];  // tri_solve sub-phases seen by warp 0: [8*bwd + {setup, fan-pre, chunks, mma, diag, fan-post, calls}]
+#define AUX_T(v) long long v = clock64()
+#define AUX_ADD(i, t0) do { if (threadIdx.x == 0) atomicAdd(&g_aux_cycles[(FWD ? 0 : 8) + (i)], (unsigned long long)(clock64() - (t0))); } while (0)
 #define PT_DECL long long pt_t0 = clock64()
 #define PT_MARK(i) do { if (threadIdx.x == 0) { long long t1_ = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(t1_ - pt_t0)); pt_t0 = t1_; } } while (0)
 #else
 #define PT_DECL
 #define PT_MARK(i)
+#define AUX_T(v)
+#define AUX_ADD(i, t0)
 #endif
 
 namespace {
@@ -55,6 +60,137 @@ __device__ __forceinline__ double warp_min(double v) {
 }
 // index of (p, q), p <= q, in the row-major upper triangle of an n x n matrix
 __device__ __forceinline__ int tri_idx(int p, int q, int n) { return p * n - (p * (p - 1)) / 2 + (q - p); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+  // ---- fantasy rows on the tensor cores -------------------------------------------------------------------
+  // Fp: rows 0..N8-1 hold F (Fp[i*8 + r] = F[r][i]), rows N8..N8+7 hold Ginv = G^-1 (Fp[(N8+kk)*8 + r] = Ginv[r][kk]).
+  // C-fragment (row g, columns 2 tg, 2 tg + 1) -> B-fragment (k = tg / tg + 4, column g) of the same 8x8 tile.
+__device__ __forceinline__ void c_to_b(double c0, double c1, int g, int tg, double& b0, double& b1) {
+    const int s0 = tg * 4 + (g >> 1), s1 = s0 + 16;
+    const double a0 = __shfl_sync(FULL, c0, s0), a1 = __shfl_sync(FULL, c1, s0);
+    const double e0 = __shfl_sync(FULL, c0, s1), e1 = __shfl_sync(FULL, c1, s1);
+    b0 = (g & 1) ? a1 : a0; b1 = (g & 1) ? e1 : e0;
+  }
+  // w_bot = Ginv^T t of one column group (t = fantasy rows of V, rows >= nfan masked): C-fragment of w_bot.
+__device__ __forceinline__ void fan_wbot(const double* V, const double* Fp, int RP, int N8, int cB, int nfan, int g, int tg, double& w0, double& w1) {
+    const double t0 = (tg < nfan) ? V[(size_t)(N8 + tg) * RP + cB] : 0.0;
+    const double t1 = (tg + 4 < nfan) ? V[(size_t)(N8 + tg + 4) * RP + cB] : 0.0;
+    w0 = 0.0; w1 = 0.0;
+    dmma(w0, w1, Fp[(size_t)(N8 + g) * 8 + tg], t0);       // A[r = g][kk = tg] = Ginv[kk][r]
+    dmma(w0, w1, Fp[(size_t)(N8 + g) * 8 + 4 + tg], t1);
+    if (g >= nfan) { w0 = 0.0; w1 = 0.0; }
+  }
+
+  // V <- L^-T V (N <= 256), every warp of the CTA working: the backward pass of the inner
+  // solve has <= 8 columns, far too few to keep a staged panel stream busy, so here the panels of L0^-1 (A-fragment order,
+  // Lbf) are read straight from L2, three tiles in flight per warp. Task = (column group, pair of block rows {c, nb-1-c}
+  // -- equal work --, row quarter). Results stay in registers until every warp has finished reading the right-hand sides.
+__device__ __noinline__ void bwd_direct(double* V, const double* Fp, const int* colidx, const double* Lbf, int RP, int N8, int nb, int ncols, int nfan, int warp, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const int g = lane >> 2, tg = lane & 3;
+    const int ngroups = (ncols + 7) >> 3, ncls = (nb + 1) >> 1, tpg = ncls * 4;
+    auto cols = [&](int group, int& cB, int& c0, int& c1, bool& v0, bool& v1) {
+      const int i0 = 8 * group, first = colidx[i0];
+      cB = (i0 + g < ncols) ? colidx[i0 + g] : first;
+      v0 = i0 + 2 * tg < ncols; v1 = i0 + 2 * tg + 1 < ncols;
+      c0 = v0 ? colidx[i0 + 2 * tg] : first; c1 = v1 ? colidx[i0 + 2 * tg + 1] : first;
+    };
+    if (nfan > 0) {
+      // top rows: v_i -= sum_r F[r][i] w_bot[r], one 8-row tile per warp-task
+      const int ntile = N8 >> 3;
+      for (int task = warp; task < ngroups * ntile; task += RBO_NWARPS) {
+        const int group = task / ntile, i0 = 8 * (task - group * ntile);
+        int cB, c0, c1; bool v0, v1;
+        cols(group, cB, c0, c1, v0, v1);
+        double w0, w1, b0, b1;
+        fan_wbot(V, Fp, RP, N8, cB, nfan, g, tg, w0, w1);
+        c_to_b(w0, w1, g, tg, b0, b1);
+        double* vr = V + (size_t)(i0 + g) * RP;
+        double x0 = vr[c0], x1 = vr[c1];
+        dmma(x0, x1, Fp[(size_t)(i0 + g) * 8 + tg], -b0);  // A[i][r = tg] = F[r][i]
+        dmma(x0, x1, Fp[(size_t)(i0 + g) * 8 + 4 + tg], -b1);
+        __syncwarp();
+        if (v0) vr[c0] = x0;
+        if (v1) vr[c1] = x1;
+      }
+      __syncthreads();
+      // fantasy rows: t -> w_bot (the products below see them only through zero coefficients)
+      for (int group = warp; group < ngroups; group += RBO_NWARPS) {
+        int cB, c0, c1; bool v0, v1;
+        cols(group, cB, c0, c1, v0, v1);
+        double w0, w1;
+        fan_wbot(V, Fp, RP, N8, cB, nfan, g, tg, w0, w1);
+        __syncwarp();
+        if (v0) V[(size_t)(N8 + g) * RP + c0] = w0;
+        if (v1) V[(size_t)(N8 + g) * RP + c1] = w1;
+      }
+    }
+    // ---- base rows: w_I = sum_{J >= I} Linv[J][I]^T b_J ; one task per warp and batch, a batch = whole column groups
+    const int gpb = RBO_NWARPS / tpg;  // column groups per batch (tpg <= RBO_NWARPS is the caller's condition)
+    for (int gb = 0; gb < ngroups; gb += gpb) {
+      const int group = gb + warp / tpg, rem = warp % tpg, cls = rem >> 2, rq = rem & 3;
+      const bool wact = warp < gpb * tpg && group < ngroups;
+      int cB = 0, c0 = 0, c1 = 0; bool v0 = false, v1 = false;
+      if (wact) cols(group, cB, c0, c1, v0, v1);
+      const int nA = wact ? nb - cls : 0;                                  // tiles of block row cls
+      const int ns = nA + ((wact && nb - 1 - cls != cls) ? cls + 1 : 0);   // ... plus those of block row nb-1-cls
+      double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      const double2* ap = nullptr; const double* vp = nullptr;
+      auto locate = [&](int s) {
+        const int hh = s >= nA, cc = hh ? s - nA : s, ib = hh ? nb - 1 - cls : cls, nc = nb - ib, rb = RBO_BR * ib;
+        const size_t chunk = (size_t)nb * ib - (size_t)ib * (ib - 1) / 2 + cc;
+        ap = reinterpret_cast<const double2*>(Lbf + (chunk * 4 + rq) * 256) + lane;
+        vp = V + (size_t)(((cc < nc - 1) ? rb + RBO_BR + cc * RBO_CHUNK_K : rb) + tg) * RP + cB;
+      };
+      auto compute = [&](const double2 (&A)[4], const double* v, bool hh) {
+        double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+          dmma(e0, e1, A[pp].x, v[(size_t)(8 * pp) * RP]);
+          dmma(o0, o1, A[pp].y, v[(size_t)(8 * pp + 4) * RP]);
+        }
+        e0 += o0; e1 += o1;
+        if (hh) { acc[1][0] += e0; acc[1][1] += e1; } else { acc[0][0] += e0; acc[0][1] += e1; }
+      };
+      __syncthreads();  // fantasy-row update of the top rows / previous batch stored
+      double2 A0[4], A1[4];
+      const double *vq0 = nullptr, *vq1 = nullptr;
+      if (0 < ns) { locate(0); vq0 = vp;
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) A0[pp] = __ldg(ap + 32 * pp); }
+      if (1 < ns) { locate(1); vq1 = vp;
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) A1[pp] = __ldg(ap + 32 * pp); }
+      for (int s = 0; s < ns; s += 2) {
+        compute(A0, vq0, s >= nA);
+        if (s + 2 < ns) { locate(s + 2); vq0 = vp;
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) A0[pp] = __ldg(ap + 32 * pp); }
+        if (s + 1 < ns) {
+          compute(A1, vq1, s + 1 >= nA);
+          if (s + 3 < ns) { locate(s + 3); vq1 = vp;
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) A1[pp] = __ldg(ap + 32 * pp); }
+        }
+      }
+      __syncthreads();  // all right-hand-side rows of this batch have been read
+      if (wact) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int ib = hh ? nb - 1 - cls : cls;
+          if (hh && ib == cls) continue;
+          const int row = RBO_BR * ib + 8 * rq + g;
+          if (row < N8) {
+            if (v0) V[(size_t)row * RP + c0] = acc[hh][0];
+            if (v1) V[(size_t)row * RP + c1] = acc[hh][1];
+          }
+        }
+      }
+    }
+  }
+
 
 struct K {
   const DevProblem& P;
@@ -372,6 +508,10 @@ struct K {
     return FWD ? P.Lf + chunk * ((size_t)ib * (ib + 1) / 2) : P.Lb + chunk * ((size_t)P.nb32 * ib - (size_t)ib * (ib - 1) / 2);
   }
 
+  // C-fragment (row g, columns 2 tg, 2 tg + 1) -> B-fragment (k = tg / tg + 4, column g) of the same 8x8 tile.
+  __device__ __forceinline__ void c_to_b(double c0, double c1, int g, int tg, double& b0, double& b1) const { rbo::c_to_b(c0, c1, g, tg, b0, b1); }
+  __device__ void bwd_direct(int ncols, int nfan) { rbo::bwd_direct(V, Fp, colidx, P.Lbf, P.RP, P.N8, P.nb32, ncols, nfan, warp, lane); }
+
   // Triangular solves of `ncols` columns of V (indices in colidx[]) against L = [L0 0; F G]:
   // FWD: V <- L^-1 V, else V <- L^-T V.
   //  * L0 lives in global memory as 32-row panels, k-major (pitch RBO_LP), 32x32 diagonal blocks pre-inverted, cut into
@@ -385,6 +525,7 @@ struct K {
   __device__ void tri_solve(int ncols, int nfan) {
     if (ncols <= 0) return;
     const int ngroups = (ncols + 7) >> 3;  // a column group = 8 consecutive entries of colidx[]
+    if (!FWD && ((P.nb32 + 1) >> 1) * 4 <= RBO_NWARPS) { bwd_direct(ncols, nfan); return; }
     if (ngroups * 4 <= RBO_NCONS) tri_solve_impl<FWD, 4>(ncols, nfan);
     else if (ngroups * 2 <= RBO_NCONS) tri_solve_impl<FWD, 2>(ncols, nfan);
     else tri_solve_impl<FWD, 1>(ncols, nfan);
@@ -400,14 +541,19 @@ struct K {
     const int nbatch = (ngroups + GPB - 1) / GPB;
     const unsigned chunks_per_pass = (unsigned)(nb * (nb + 1) / 2);
     const int ncons = min(ngroups, GPB) * NRQ;  // consumer warps of this pass: warps 0 .. ncons-1
+    AUX_T(ts0_);
     pipe_setup(ncons);
+    AUX_ADD(0, ts0_);
+#ifdef RBO_PHASE_TIMERS
+    if (tid == 0) atomicAdd(&g_aux_cycles[(FWD ? 0 : 8) + 6], 1ull);
+#endif
     if (warp == RBO_NCONS) {
       // ---------------- producer warp ----------------
       if (lane == 0) {
         unsigned q = qglob;
         for (int bt = 0; bt < nbatch; ++bt)
           for (int i = 0; i < nb; ++i) {
-            const int ib = FWD ? i : nb - 1 - i, nc = FWD ? ib + 1 : nb - ib;
+            const int ib = FWD ? nb - 1 - i : i, nc = FWD ? ib + 1 : nb - ib;
             const double* src = pan_ptr<FWD>(ib);
             for (int c = 0; c < nc; ++c, ++q) {
               if (q >= RBO_NSTAGE) empty_wait(q);
@@ -436,6 +582,7 @@ struct K {
       double* fv = V + cB;
       const int fp = tg;
 
+      AUX_T(tf0_);
       if (!FWD && nfan > 0 && wact) {
         if (rq == 0) {
           // w_bot = Ginv^T t restricted to the active rows: w_r = sum_kk Ginv[kk][r] t[kk], Ginv[kk][r] = Fp[(N8 + r)*8 + kk]
@@ -465,12 +612,16 @@ struct K {
         group_sync(NRQ, gl);
       }
 
+      AUX_ADD(1, tf0_);
+      AUX_T(tc0_);
       double c[MTW][2];
 #pragma unroll
       for (int mt = 0; mt < MTW; ++mt) { c[mt][0] = 0.0; c[mt][1] = 0.0; }
       const int rofs = 8 * MTW * rq;  // first row (within a panel) owned by this warp
       for (int i = 0; i < nb; ++i) {
-        const int ib = FWD ? i : nb - 1 - i, nc = FWD ? ib + 1 : nb - ib, rb = RBO_BR * ib;
+        // explicit-inverse panels: block row ib of the result only needs RIGHT-HAND-SIDE rows (blocks <= ib forward, >= ib
+        // backward), so the block rows are visited in the order that overwrites a block only after its last use as input
+        const int ib = FWD ? nb - 1 - i : i, nc = FWD ? ib + 1 : nb - ib, rb = RBO_BR * ib;
         for (int cc = 0; cc < nc; ++cc, ++q) {
 #ifdef RBO_PHASE_TIMERS
           long long tw0 = clock64();
@@ -480,14 +631,15 @@ struct K {
           if (tid == 0) atomicAdd(&g_phase_cycles[FWD ? 12 : 13], (unsigned long long)(clock64() - tw0));
 #endif
           const double* buf = stage + (size_t)(q % RBO_NSTAGE) * RBO_CHUNK_K * RBO_LP + rofs;
+          AUX_T(tm0_);
           if (wact) {
             if (cc < nc - 1) {
               const int krow0 = (FWD ? 0 : rb + RBO_BR) + cc * RBO_CHUNK_K;  // V row of the first k of this chunk
               mma_chunk<MTW>(buf, V + (size_t)krow0 * RP, cB, g, tg, c);
             } else {
-              // last chunk of the panel = inverted diagonal block applied to the panel's own right-hand-side rows; the
-              // off-diagonal chunks were pre-multiplied by it and negated on the host, so c now holds the solved rows
+              // last chunk of the panel = diagonal block of the inverse applied to the panel's own right-hand-side rows
               mma_chunk<MTW>(buf, V + (size_t)rb * RP, cB, g, tg, c);
+              AUX_T(td0_);
               group_sync(NRQ, gl);  // every warp of the group has read the right-hand-side rows
 #pragma unroll
               for (int mt = 0; mt < MTW; ++mt) {
@@ -498,37 +650,39 @@ struct K {
                 }
                 c[mt][0] = 0.0; c[mt][1] = 0.0;
               }
-              group_sync(NRQ, gl);  // solved rows visible to the group before they feed later panels
+              asm volatile("" ::: "memory");  // keeps the stores of this panel ahead of the next panel's loads in program order (and the register allocation compact)
+              AUX_ADD(4, td0_);
             }
           }
           __syncwarp();
+          AUX_ADD(3, tm0_);
           if (lane == 0) empty_arrive(q);
         }
       }
 
+      AUX_ADD(2, tc0_);
       if (FWD && nfan > 0 && wact && rq == 0) {
-        double a8[8], t[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) a8[r] = 0.0;
-        fan_rows(Fp, N8, fp, fv, a8);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          a8[r] += __shfl_xor_sync(FULL, a8[r], 1);
-          a8[r] += __shfl_xor_sync(FULL, a8[r], 2);
+        // a = F v_top on the tensor cores (four interleaved accumulator chains), t = b_bot - a, v_bot = Ginv t
+        double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
+        const double* fa = Fp + (size_t)tg * 8 + g;          // A[r = g][k = i] = F[r][i] = Fp[i*8 + r]
+        const double* vb = V + (size_t)tg * RP + cB;
+        const int nkt = N8 >> 2;  // even (N8 is a multiple of 8)
+#pragma unroll 2
+        for (int kt = 0; kt < nkt; kt += 2) {
+          dmma(a0[0], a1[0], fa[(size_t)(4 * kt) * 8], vb[(size_t)(4 * kt) * RP]);
+          dmma(a0[1], a1[1], fa[(size_t)(4 * kt + 4) * 8], vb[(size_t)(4 * kt + 4) * RP]);
         }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) t[r] = fv[(size_t)(N8 + r) * RP] - a8[r];
+        const double s0 = a0[0] + a0[1], s1 = a1[0] + a1[1];
+        double* vr = V + (size_t)(N8 + g) * RP;
+        const double t0 = (g < nfan) ? vr[c0] - s0 : 0.0, t1 = (g < nfan) ? vr[c1] - s1 : 0.0;
+        double b0, b1, r0 = 0.0, r1 = 0.0;
+        c_to_b(t0, t1, g, tg, b0, b1);
+        dmma(r0, r1, Fp[(size_t)(N8 + tg) * 8 + g], b0);       // A[r = g][kk = tg] = Ginv[r][kk]
+        dmma(r0, r1, Fp[(size_t)(N8 + tg + 4) * 8 + g], b1);
+        if (g >= nfan) { r0 = 0.0; r1 = 0.0; }
         __syncwarp();
-        // v_r = sum_kk Ginv[r][kk] t[kk] (Ginv stored k-major at Fp[(N8 + kk)*8 + r]); lane fp computes rows fp and fp + 4
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const int r = fp + 4 * h2;
-          double s = 0.0;
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) s = fma(Fp[(size_t)(N8 + kk) * 8 + r], t[kk], s);
-          if (r >= nfan) s = 0.0;
-          if (vB) fv[(size_t)(N8 + r) * RP] = s;
-        }
+        if (v0) vr[c0] = r0;
+        if (v1) vr[c1] = r1;
         __syncwarp();
       }
     }
@@ -1403,6 +1557,12 @@ extern "C" int rbo_debug_phase_cycles(void*, unsigned long long* out16, int rese
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out16, rbo::g_phase_cycles, sizeof(unsigned long long) * 16);
   if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(rbo::g_phase_cycles, z, sizeof(z)); }
+  return 0;
+}
+extern "C" int rbo_debug_aux_cycles(void*, unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, rbo::g_aux_cycles, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(rbo::g_aux_cycles, z, sizeof(z)); }
   return 0;
 }
 #endif

@@ -24,6 +24,10 @@ def main(name="C3", M=296):
     fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
     s = eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), vals, gx, gt, dual_dirs=dd)
     fn(eng.handle.h, out, 1)
+    aux = (ctypes.c_ulonglong * 16)()
+    fa = eng.lib.rbo_debug_aux_cycles
+    fa.argtypes = fn.argtypes
+    fa(eng.handle.h, aux, 1)
     s = eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), vals, gx, gt, dual_dirs=dd)
     fn(eng.handle.h, out, 1)
     tot = sum(out[i] for i in range(12))
@@ -32,6 +36,12 @@ def main(name="C3", M=296):
     for i in range(15):
         if NAMES[i] != "-":
             print(f"  {NAMES[i]:<16} {100 * out[i] / tot:5.1f}%   {out[i] / max(rounds, 1):9.0f} cycles/round")
+    fa(eng.handle.h, aux, 0)
+    AN = ["setup", "fan-pre", "chunk loop", "  mma+store", "  diag sync+store", "-", "calls(x cycles~1)", "-"]
+    for half, nm in ((0, "fwd"), (8, "bwd")):
+        for i in range(7):
+            if AN[i] != "-":
+                print(f"  {nm} {AN[i]:<18} {aux[half + i] / max(rounds, 1):9.0f} cycles/round")
     eng.close()
 
 if __name__ == "__main__":
