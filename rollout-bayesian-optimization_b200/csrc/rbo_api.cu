@@ -140,7 +140,7 @@ int rbo_create(rbo_handle** out, int device_id) {
   h->stream = h->own_stream;
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
-  CKC(cudaMalloc((void**)&h->work_counter, sizeof(int)));
+  CKC(cudaMalloc((void**)&h->work_counter, 16 * sizeof(int)));  // [0] trajectory scheduler, [1..2] kernel watchdog flags
   CKC(cudaMalloc((void**)&h->sobol_dirs, sizeof(rbo_sobol_dirs_host)));
   CKC(cudaMemcpy(h->sobol_dirs, rbo_sobol_dirs_host, sizeof(rbo_sobol_dirs_host), cudaMemcpyHostToDevice));
   CKC(cudaFuncSetAttribute(rbo_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
@@ -382,7 +382,7 @@ static int ensure_outputs(rbo_handle* h, int M, int hor, int S, int d, int nth) 
 }
 
 // Chooses the number of start slots W (starts evaluated in lock-step) so that the shared-memory plan fits.
-struct PlanChoice { int W, RP, NR, RSmax, NPmax, xsm; size_t bytes; };
+struct PlanChoice { int W, RP, NR, RSmax, NPmax, xsm; size_t bytes; int RSh; };
 static bool choose_plan(const rbo_handle* h, int hor, int S, PlanChoice* pc) {
   const int d = h->d, N8 = h->N8, CS = d + 3, NR = std::max(N8 + RBO_MAXFAN, h->nb32 * RBO_BR);
   const int nadj = ncols_adjoint(d);
@@ -392,10 +392,16 @@ static bool choose_plan(const rbo_handle* h, int hor, int S, PlanChoice* pc) {
     int RP = std::max(W * CS, nadj) + 2;
     if ((RP & 1) == 0) RP += 1;  // odd pitch: conflict-free column walks
     int NPmax = npairs_max(d, W);
-    SmemPlan pl = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm);
+    SmemPlan pl = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm, RSmax);
     size_t bytes = (size_t)pl.total * 8;
     if (bytes > (size_t)h->max_smem) return false;
-    *pc = {W, RP, NR, RSmax, NPmax, xsm, bytes};
+    *pc = {W, RP, NR, RSmax, NPmax, xsm, bytes, RSmax};
+    // the Hessian sums are tensor-pipe bound per scheduler: give them enough row splits to occupy every warp if that still fits
+    const int want = std::min(4, std::max(RSmax, RBO_NWARPS / W));
+    for (int rsh = want; rsh > RSmax; --rsh) {
+      SmemPlan p2 = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm, rsh);
+      if ((size_t)p2.total * 8 <= (size_t)h->max_smem) { pc->RSh = rsh; pc->bytes = (size_t)p2.total * 8; break; }
+    }
     return true;
   };
   const int Wmax = std::min(S, RBO_NCONS);
@@ -439,11 +445,14 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   if (!choose_plan(h, horizon, S, &pc))
     return fail(h, RBO_ERR_UNSUPPORTED, "rbo_rollout: problem (d=%d, N=%d, h=%d) needs more than %d bytes of shared memory per CTA", h->d, h->N, horizon, h->max_smem);
   if (getenv("RBO_DEBUG")) fprintf(stderr, "[rbo] plan: W=%d RP=%d NR=%d RSmax=%d NPmax=%d xsm=%d smem=%zu B (limit %d)\n", pc.W, pc.RP, pc.NR, pc.RSmax, pc.NPmax, pc.xsm, pc.bytes, h->max_smem);
+  if (getenv("RBO_DEBUG")) fprintf(stderr, "[rbo] plan: RSh=%d\n", pc.RSh);
   int rc = ensure_outputs(h, M, horizon, S, h->d, ntheta);
   if (rc) return rc;
   DevProblem P;
   memset(&P, 0, sizeof(P));
   P.d = h->d; P.N = h->N; P.N8 = h->N8; P.nb8 = h->nb8; P.nb32 = h->nb32; P.h = horizon; P.S = S; P.W = pc.W; P.RSmax = pc.RSmax; P.NPmax = pc.NPmax; P.xsm = pc.xsm; P.XP = h->N8 + 1;
+  P.RSh = pc.RSh;
+  P.pl = make_plan(P.d, P.N8, horizon, pc.W, pc.RP, pc.NR, pc.RSmax, pc.NPmax, pc.xsm, pc.RSh);
   P.CS = h->d + 3; P.RP = pc.RP; P.NR = pc.NR; P.M = M; P.hp1 = h->hp1; P.mode = mode; P.flags = flags; P.ntheta = ntheta;
   P.kern = h->kern; P.rule_id = h->rule_id; P.sigma_tol = h->sigma_tol; P.sigma_n2 = h->sigma_n2; P.k0 = h->k0; P.d2k0 = h->d2k0;
   P.ymin_base = h->ymin_base; P.m52_c = std::sqrt(5.0) / h->kern.th[0]; P.fmini = fmini; P.theta1 = theta[0]; P.htol = h->htol; P.so = h->so;
@@ -461,7 +470,7 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
     if (h->tape_cap < need) { CK(h, dev_realloc(&h->cs_tape, need)); h->tape_cap = need; }
     P.cs_tape = h->cs_tape;
   }
-  CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
+  CK(h, cudaMemsetAsync(h->work_counter, 0, 16 * sizeof(int), h->stream));
   CK(h, cudaEventRecord(h->ev0, h->stream));
   rbo_rollout_kernel<<<grid, RBO_THREADS, pc.bytes, h->stream>>>(P);
   CK(h, cudaGetLastError());
@@ -472,8 +481,13 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   h->last_h = horizon; h->last_mode = mode; h->last_nth = ntheta;
   if (want_summary && summary) {
     std::vector<double> sums(h->sums_len);
+    int wd[16] = {0};
     CK(h, cudaMemcpyAsync(sums.data(), h->sums, (size_t)h->sums_len * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(wd, h->work_counter, sizeof(wd), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    if (wd[1] || wd[2])
+      return fail(h, RBO_ERR_CUDA, "rollout kernel watchdog: %s%s (wait kind %d, chunk %d, warp %d, consumers %d, block %d)", wd[1] ? "[panel pipeline wait never completed] " : "",
+                  wd[2] ? "[inner solve exceeded its evaluation bound]" : "", wd[4], wd[5], wd[6], wd[7], wd[8]);
     float ms = 0;
     CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     const int d = h->d, hh = std::max(horizon, 1), nrows = 1 + d + ntheta;

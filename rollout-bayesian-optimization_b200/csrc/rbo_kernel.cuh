@@ -4,6 +4,18 @@
 
 namespace rbo {
 
+// Shared-memory plan (offsets in doubles from the start of dynamic shared memory).
+struct SmemPlan {
+  int V, Fp, G, u, Xf, yf, gyf, Xs, stage, mbar;
+  int sx, sxt, sg, sH, sA, sp;               // per slot: x, trial x, gradient, Hessian, Cholesky scratch, step
+  int sHt, sHref, sga, sdmu, sdsig, sgh;     // per slot: trial Hessian (-H alpha), reference H alpha, grad alpha, grad mu, grad sigma, scalars
+  int sf, slam, spred, shs;                  // per slot scalars
+  int ppre, ppost, ppost1, phess;            // partial sums of the row reductions
+  int bestx, misc, adj;                      // [d] best candidate ; scalar/scratch area ; adjoint duals
+  int pairs, tbl, ints;                      // int areas (in doubles)
+  int total;                                 // total doubles
+};
+
 // Everything the rollout kernel needs, passed by value as a __grid_constant__ parameter.
 struct DevProblem {
   // sizes
@@ -12,6 +24,7 @@ struct DevProblem {
   int h, S, W;            // horizon; start columns; start slots evaluated together in one lock-step round
   int CS, RP, NR;         // columns per start slot (d+3); padded V row pitch (doubles); V rows (N8 + RBO_MAXFAN)
   int RSmax, NPmax;       // row splits of the reductions; capacity of the pair list
+  int RSh;                // row splits of the Hessian sums (>= RSmax when shared memory allows)
   int xsm, XP;            // base locations staged in shared memory (1) or read through L1 (0); their row pitch
   int M;                  // trajectories owned by this handle
   int hp1;                // third dimension of the normals tensor
@@ -55,18 +68,7 @@ struct DevProblem {
   int* start_iters;    // [M][h][S]
   int* work_counter;   // dynamic trajectory scheduler
   double* cs_tape;     // [gridDim.x][h+2][NR] coefficient tape of the trajectory each CTA is working on
-};
-
-// Shared-memory plan (offsets in doubles from the start of dynamic shared memory).
-struct SmemPlan {
-  int V, Fp, G, u, Xf, yf, gyf, Xs, stage, mbar;
-  int sx, sxt, sg, sH, sA, sp;               // per slot: x, trial x, gradient, Hessian, Cholesky scratch, step
-  int sHt, sHref, sga, sdmu, sdsig, sgh;     // per slot: trial Hessian (-H alpha), reference H alpha, grad alpha, grad mu, grad sigma, scalars
-  int sf, slam, spred, shs;                  // per slot scalars
-  int ppre, ppost, ppost1, phess;            // partial sums of the row reductions
-  int bestx, misc, adj;                      // [d] best candidate ; scalar/scratch area ; adjoint duals
-  int pairs, tbl, ints;                      // int areas (in doubles)
-  int total;                                 // total doubles
+  SmemPlan pl;         // make_plan(...) evaluated on the host: the offsets are then constant-bank operands in the kernel
 };
 
 __host__ __device__ inline int ncols_adjoint(int d) { return 4 * (d + 1) + 2; }
@@ -75,7 +77,7 @@ __host__ __device__ inline int npairs_max(int d, int W) {
   return a > b ? a : b;
 }
 
-__host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int RP, int NR, int RSmax, int NPmax, int xsm) {
+__host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int RP, int NR, int RSmax, int NPmax, int xsm, int RSh) {
   SmemPlan p;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };  // keep 16-byte alignment
@@ -96,7 +98,7 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.ppre = take(RSmax * W * q1);
   p.ppost = take(RSmax * NPmax);
   p.ppost1 = take(RSmax * W * q1);
-  p.phess = take(RSmax * W * 2 * (T2 + 1));
+  p.phess = take(RSh * W * 2 * (T2 + 1));
   p.bestx = take(d);
   p.misc = take(64 + 2 * q1 * q1 + 2 * q1);
   p.adj = take(19 * d + 32);

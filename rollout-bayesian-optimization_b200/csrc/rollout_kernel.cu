@@ -42,6 +42,9 @@ namespace {
 // int-area layout
 enum { I_M = 0, I_NACT = 1, I_TSTATUS = 2, I_BEST = 3, I_EVALS = 4, I_T = 5, I_CASE = 6, I_NEXT = 7, I_ARR = 64 };
 constexpr unsigned FULL = 0xffffffffu;
+#ifndef RBO_SPIN_CAP
+#define RBO_SPIN_CAP (1u << 28)  // polls of an mbarrier before the wait is declared dead (seconds; a healthy wait takes microseconds)
+#endif
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -194,7 +197,7 @@ __device__ __noinline__ void bwd_direct(double* V, const double* Fp, const int* 
 
 struct K {
   const DevProblem& P;
-  SmemPlan pl;
+  const SmemPlan& pl;
   double* sm;
   int* si;
   int tid, lane, warp;
@@ -207,8 +210,7 @@ struct K {
   int pipe_ncons;  // consumer warps the empty barriers currently expect (0 = not initialised)
   int *alist, *phase, *sstat, *siter, *stry, *sstart, *sevals, *sfr, *colidx, *items, *tbld;
 
-  __device__ K(const DevProblem& P_, double* sm_) : P(P_), sm(sm_) {
-    pl = make_plan(P.d, P.N8, P.h, P.W, P.RP, P.NR, P.RSmax, P.NPmax, P.xsm);
+  __device__ K(const DevProblem& P_, double* sm_) : P(P_), pl(P_.pl), sm(sm_) {
     tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
     nf = 0;
     CCOL = P.RP - 1; UCOL = P.RP - 2;
@@ -261,8 +263,12 @@ struct K {
         continue;
       }
       const double* x = pt(s);
+      // coordinates of row j: base rows are coordinate-major (stride XP in shared memory / N8 in global), fantasy rows point-major
+      const bool base = j < P.N8;
+      const double* xc = base ? (P.xsm ? Xs + j : P.Xb + j) : Xf + (j - P.N8) * d;
+      const int xst = base ? (P.xsm ? P.XP : P.N8) : 1;
       double rho2 = 0.0;
-      for (int p = 0; p < d; ++p) { double r = x[p] - xcoord(j, p); rho2 = fma(r, r, rho2); }
+      for (int p = 0; p < d; ++p) { double r = x[p] - xc[p * xst]; rho2 = fma(r, r, rho2); }
       double psi, a, b, gb;
       if (P.kern.id == RBO_KERNEL_MATERN52) {
         // closed forms without divisions: b = psi'/rho = -(c^2/3)(1+s)e^-s, a = (psi'' - b)/rho^2 = (c^4/3) e^-s; at rho = 0 they
@@ -275,7 +281,7 @@ struct K {
         kern_radial(P.kern, rho2, psi, a, b, gb);
       }
       row[0] = psi;
-      for (int p = 0; p < d; ++p) row[1 + p] = b * (x[p] - xcoord(j, p));
+      for (int p = 0; p < d; ++p) row[1 + p] = b * (x[p] - xc[p * xst]);
       row[d + 1] = a;
       row[d + 2] = b;
     }
@@ -360,32 +366,61 @@ struct K {
       const int colab = cab(s) + d + 1, colw = cw(s);
       const int p0 = min(16 * mb + g, d - 1), p1 = min(16 * mb + 8 + g, d - 1), q0 = min(16 * nk + g, d - 1), q1_ = min(16 * nk + 8 + g, d - 1);
       const double xp0 = x[p0], xp1 = x[p1], xq0 = x[q0], xq1 = x[q1_];
+      const bool diag = mb == nk;                                       // diagonal block: q == p, and the (p1, q0) tile lies below the diagonal
+      const bool hiP = d - 16 * mb > 8, hiQ = d - 16 * nk > 8;        // second 8-wide tile in use (warp-uniform)
       double cC[4][2], cW[4][2], bC = 0.0, bW = 0.0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) { cC[i][0] = cC[i][1] = 0.0; cW[i][0] = cW[i][1] = 0.0; }
-#pragma unroll 2
-      for (int j0 = 4 * rs; j0 < nrows; j0 += 4 * RS) {
-        const int j = j0 + tg;
-        const bool in = j < nrows;
-        const int jj = in ? j : 0;
+      // base rows: coordinates straight from the coordinate-major table (shared or global), no per-element branching
+      const int xst = P.xsm ? P.XP : P.N8;
+      const int op0 = p0 * xst, op1 = p1 * xst, oq0 = q0 * xst, oq1 = q1_ * xst;
+      const int nbase4 = P.N8 & ~3;
+      auto body = [&](int jj, bool in, double rp0, double rp1, double rq0, double rq1) {
         const double* row = V + (size_t)jj * RP;
         const double aj = in ? row[colab] : 0.0, bj = in ? row[colab + 1] : 0.0;
         const double wj = (MASK & 2) ? row[colw] : 0.0, cj = (MASK & 1) ? row[CCOL] : 0.0;
         const double ca = cj * aj, wa = wj * aj;
-        const double rp0 = xp0 - xcoord(jj, p0), rp1 = xp1 - xcoord(jj, p1), rq0 = xq0 - xcoord(jj, q0), rq1 = xq1 - xcoord(jj, q1_);
         if (g == 0) { bC = fma(cj, bj, bC); bW = fma(wj, bj, bW); }
         if (MASK & 1) {
           dmma(cC[0][0], cC[0][1], ca * rp0, rq0);
-          dmma(cC[1][0], cC[1][1], ca * rp0, rq1);
-          dmma(cC[2][0], cC[2][1], ca * rp1, rq0);
-          dmma(cC[3][0], cC[3][1], ca * rp1, rq1);
+          if (hiQ) dmma(cC[1][0], cC[1][1], ca * rp0, rq1);
+          if (hiP) {
+            if (!diag) dmma(cC[2][0], cC[2][1], ca * rp1, rq0);
+            if (hiQ) dmma(cC[3][0], cC[3][1], ca * rp1, rq1);
+          }
         }
         if (MASK & 2) {
           dmma(cW[0][0], cW[0][1], wa * rp0, rq0);
-          dmma(cW[1][0], cW[1][1], wa * rp0, rq1);
-          dmma(cW[2][0], cW[2][1], wa * rp1, rq0);
-          dmma(cW[3][0], cW[3][1], wa * rp1, rq1);
+          if (hiQ) dmma(cW[1][0], cW[1][1], wa * rp0, rq1);
+          if (hiP) {
+            if (!diag) dmma(cW[2][0], cW[2][1], wa * rp1, rq0);
+            if (hiQ) dmma(cW[3][0], cW[3][1], wa * rp1, rq1);
+          }
         }
+      };
+      int j0 = 4 * rs;
+      if (P.xsm) {
+#pragma unroll 2
+        for (; j0 < nbase4; j0 += 4 * RS) {
+          const int j = j0 + tg;
+          const double rp0 = xp0 - Xs[op0 + j], rp1 = xp1 - Xs[op1 + j];
+          const double rq0 = diag ? rp0 : xq0 - Xs[oq0 + j], rq1 = diag ? rp1 : xq1 - Xs[oq1 + j];
+          body(j, true, rp0, rp1, rq0, rq1);
+        }
+      } else {
+#pragma unroll 2
+        for (; j0 < nbase4; j0 += 4 * RS) {
+          const int j = j0 + tg;
+          const double rp0 = xp0 - __ldg(P.Xb + op0 + j), rp1 = xp1 - __ldg(P.Xb + op1 + j);
+          const double rq0 = diag ? rp0 : xq0 - __ldg(P.Xb + oq0 + j), rq1 = diag ? rp1 : xq1 - __ldg(P.Xb + oq1 + j);
+          body(j, true, rp0, rp1, rq0, rq1);
+        }
+      }
+      for (; j0 < nrows; j0 += 4 * RS) {  // last base rows (N8 not a multiple of 4 never happens; kept general) and the fantasy rows
+        const int j = j0 + tg;
+        const bool in = j < nrows;
+        const int jj = in ? j : 0;
+        body(jj, in, xp0 - xcoord(jj, p0), xp1 - xcoord(jj, p1), xq0 - xcoord(jj, q0), xq1 - xcoord(jj, q1_));
       }
       bC += __shfl_xor_sync(FULL, bC, 1); bC += __shfl_xor_sync(FULL, bC, 2);
       bW += __shfl_xor_sync(FULL, bW, 1); bW += __shfl_xor_sync(FULL, bW, 2);
@@ -445,7 +480,9 @@ struct K {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
   }
-  __device__ __forceinline__ void mbar_wait(unsigned mb, unsigned parity) {
+  // consumer side: plain spin on the full barrier (hot path)
+  __device__ __forceinline__ void full_wait(unsigned q) {
+    const unsigned mb = smem_u32(&mbar[q % RBO_NSTAGE]), parity = (q / RBO_NSTAGE) & 1u;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -454,9 +491,22 @@ struct K {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(mb), "r"(parity) : "memory");
   }
-  __device__ __forceinline__ void full_wait(unsigned q) { mbar_wait(smem_u32(&mbar[q % RBO_NSTAGE]), (q / RBO_NSTAGE) & 1u); }
-  __device__ __forceinline__ void empty_wait(unsigned q) {  // producer: stage of chunk q was released by all consumers of chunk q - NSTAGE
-    mbar_wait(smem_u32(&mbar[RBO_NSTAGE + q % RBO_NSTAGE]), ((q / RBO_NSTAGE) - 1u) & 1u);
+  // producer side: stage of chunk q was released by all consumers of chunk q - NSTAGE. Bounded spin: a release that never
+  // comes is a protocol bug; it is recorded (the host reports the launch as failed) and the producer carries on, so the
+  // consumers still receive every chunk and the kernel terminates instead of hanging the GPU.
+  __device__ __forceinline__ void empty_wait(unsigned q) {
+    const unsigned mb = smem_u32(&mbar[RBO_NSTAGE + q % RBO_NSTAGE]), parity = ((q / RBO_NSTAGE) - 1u) & 1u;
+    for (unsigned spins = 0; spins < RBO_SPIN_CAP; ++spins) {
+      unsigned ok;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(mb), "r"(parity) : "memory");
+      if (ok) return;
+    }
+    if (atomicExch(P.work_counter + 1, 1) == 0) {
+      P.work_counter[4] = 2; P.work_counter[5] = (int)q; P.work_counter[6] = warp; P.work_counter[7] = pipe_ncons; P.work_counter[8] = blockIdx.x;
+    }
   }
   __device__ __forceinline__ void empty_arrive(unsigned q) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&mbar[RBO_NSTAGE + q % RBO_NSTAGE])) : "memory");
@@ -901,7 +951,10 @@ struct K {
     __syncthreads();
     int nact = si[I_NACT];
     PT_DECL;
+    const long long round_cap = (long long)P.S * (P.so.maxit + 2) * (P.so.maxtry + 2);  // no start can use more evaluations than that
+    long long rounds_ = 0;
     while (nact > 0) {
+      if (++rounds_ > round_cap) { if (tid == 0) P.work_counter[2] = 1; break; }
       auto pt = [&](int s) { return (const double*)(sm + pl.sxt + alist[s] * d); };
       auto cb = [&](int s) { return alist[s] * P.CS; };
       PT_MARK(9);
@@ -964,7 +1017,7 @@ struct K {
       __syncthreads();
       PT_MARK(4);
       const int nbd = nblk16(d);
-      const int RShw = choose_rs(nact * nbd * (nbd + 1) / 2), RShc = RShw;
+      const int RShw = max(1, min(P.RSh, RBO_NWARPS / (nact * (nbd * (nbd + 1) / 2)))), RShc = RShw;  // row splits: enough to occupy every warp
       hess_sums<3>(nact, pt, cb, cb, RShw);
       __syncthreads();
       PT_MARK(5);

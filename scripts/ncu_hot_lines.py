@@ -24,7 +24,10 @@ for r in rows:
     a["shw"] += g("L1 Wavefronts Shared"); a["shi"] += g("L1 Wavefronts Shared Ideal")
 ti = sum(a["inst"] for a in agg.values()); ts = sum(a["smp"] for a in agg.values())
 print(f"total warp instructions {ti:.3e}, samples {ts:.0f}")
-for title, key in (("samples", "smp"), ("instructions", "inst")):
+for a in agg.values(): a["busy"] = a["smp"] - a["bar"]
+tb = sum(a["busy"] for a in agg.values())
+print(f"non-barrier samples {tb:.0f} ({100*tb/ts:.1f}% of all)")
+for title, key in (("samples", "smp"), ("non-barrier samples", "busy"), ("instructions", "inst")):
     print(f"--- top {topn} lines by {title}")
     for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][key])[:topn]:
-        print(f"{f}:{l:>4} smp {100*a['smp']/ts:5.1f}% inst {100*a['inst']/ti:5.1f}% [bar {100*a['bar']/max(a['smp'],1):3.0f}% lsb {100*a['lsb']/max(a['smp'],1):3.0f}% ssb {100*a['ssb']/max(a['smp'],1):3.0f}% wait {100*a['wait']/max(a['smp'],1):3.0f}%] shw/ideal {a['shw']/max(a['shi'],1):.1f} | {a['src'][:100]}")
+        print(f"{f}:{l:>4} busy {100*a['busy']/max(tb,1):5.1f}% smp {100*a['smp']/ts:5.1f}% inst {100*a['inst']/ti:5.1f}% [bar {100*a['bar']/max(a['smp'],1):3.0f}% lsb {100*a['lsb']/max(a['smp'],1):3.0f}% ssb {100*a['ssb']/max(a['smp'],1):3.0f}% wait {100*a['wait']/max(a['smp'],1):3.0f}%] shw/ideal {a['shw']/max(a['shi'],1):.1f} | {a['src'][:100]}")
