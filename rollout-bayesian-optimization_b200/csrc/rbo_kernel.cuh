@@ -73,7 +73,7 @@ struct DevProblem {
 
 __host__ __device__ inline int ncols_adjoint(int d) { return 4 * (d + 1) + 2; }
 __host__ __device__ inline int npairs_max(int d, int W) {
-  int q1 = d + 1, a = W * q1 * q1, b = 2 * q1 * q1 + 2 * q1;  // outputs of the largest column-product call
+  int q1 = d + 1, a = W * q1 * (q1 + 1), b = 2 * q1 * q1 + 2 * q1;  // outputs of the largest column-product call
   return a > b ? a : b;
 }
 
@@ -97,12 +97,12 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.sf = take(W); p.slam = take(W); p.spred = take(W); p.shs = take(W);
   p.ppre = take(RSmax * W * q1);
   p.ppost = take(RSmax * NPmax);
-  p.ppost1 = take(RSmax * W * q1);
+  p.ppost1 = take(0 * RSmax * W * q1);  // only the (disabled) overlap variant of the inner solve uses it
   p.phess = take(RSh * W * 2 * (T2 + 1));
   p.bestx = take(d);
   p.misc = take(64 + 2 * q1 * q1 + 2 * q1);
   p.adj = take(19 * d + 32);
-  p.pairs = take((5 * (W + 2) + 1) / 2);  // product items
+  p.pairs = take((6 * (W + 2) + 1) / 2);  // product items
   p.tbl = take((T2 + 2) / 2 + 1);
   p.ints = take(64 + 10 * W + 32 * W / 2 + (ncols_adjoint(d) + W * q1 + 1) / 2);
   p.total = o;

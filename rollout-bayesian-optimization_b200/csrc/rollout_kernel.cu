@@ -207,7 +207,6 @@ struct K {
   double* cst;     // this CTA's coefficient tape in global memory: cst[k * NR + j] = cs[k][j] (rbs.jl:326)
   unsigned long long* mbar;
   unsigned qglob;  // running count of staged panel chunks (ring position and mbarrier parity)
-  int pipe_ncons;  // consumer warps the empty barriers currently expect (0 = not initialised)
   int *alist, *phase, *sstat, *siter, *stry, *sstart, *sevals, *sfr, *colidx, *items, *tbld;
 
   __device__ K(const DevProblem& P_, double* sm_) : P(P_), pl(P_.pl), sm(sm_) {
@@ -215,7 +214,7 @@ struct K {
     nf = 0;
     CCOL = P.RP - 1; UCOL = P.RP - 2;
     V = sm + pl.V; Fp = sm + pl.Fp; G = sm + pl.G; u = sm + pl.u; Xs = sm + pl.Xs; stage = sm + pl.stage;
-    mbar = reinterpret_cast<unsigned long long*>(sm + pl.mbar); qglob = 0; pipe_ncons = 0;
+    mbar = reinterpret_cast<unsigned long long*>(sm + pl.mbar); qglob = 0;
     cst = P.cs_tape + (size_t)blockIdx.x * (P.h + 2) * P.NR;
     Xf = sm + pl.Xf; yf = sm + pl.yf; gyf = sm + pl.gyf; misc = sm + pl.misc; adj = sm + pl.adj; bestx = sm + pl.bestx;
     si = reinterpret_cast<int*>(sm + pl.ints);
@@ -299,9 +298,10 @@ struct K {
     int rs = nw / (nblocks > 0 ? nblocks : 1);
     return rs < 1 ? 1 : (rs > P.RSmax ? P.RSmax : rs);
   }
-  __device__ __forceinline__ void set_item(int i, int colA, int na, int colB, int nb, int out) {
-    int* it = items + 5 * i;
-    it[0] = colA; it[1] = na; it[2] = colB; it[3] = nb; it[4] = out;
+  // xcol >= 0: the LAST of the nb B-columns is column xcol of V instead of colB + nb - 1
+  __device__ __forceinline__ void set_item(int i, int colA, int na, int colB, int nb, int out, int xcol = -1) {
+    int* it = items + 6 * i;
+    it[0] = colA; it[1] = na; it[2] = colB; it[3] = nb; it[4] = out; it[5] = xcol;
   }
   __device__ static __forceinline__ int nblk16(int n) { return (n + 15) >> 4; }
 
@@ -309,17 +309,18 @@ struct K {
   __device__ void colprod(int nitems, int nout, double* dst, int RS, int wbase = 0, int nw = RBO_NWARPS) {
     const int RP = P.RP, nrows = P.N8 + nf, g = lane >> 2, tg = lane & 3;
     int ntask = 0;
-    for (int i = 0; i < nitems; ++i) ntask += nblk16(items[5 * i + 1]) * nblk16(items[5 * i + 3]);
+    for (int i = 0; i < nitems; ++i) ntask += nblk16(items[6 * i + 1]) * nblk16(items[6 * i + 3]);
     if (warp < wbase || warp >= wbase + nw) return;
     for (int task = warp - wbase; task < ntask * RS; task += nw) {
       int t = task / RS;
       const int rs = task - t * RS;
       int i = 0, nbA, nbB;
-      for (;; ++i) { nbA = nblk16(items[5 * i + 1]); nbB = nblk16(items[5 * i + 3]); if (t < nbA * nbB) break; t -= nbA * nbB; }
-      const int* it = items + 5 * i;
+      for (;; ++i) { nbA = nblk16(items[6 * i + 1]); nbB = nblk16(items[6 * i + 3]); if (t < nbA * nbB) break; t -= nbA * nbB; }
+      const int* it = items + 6 * i;
       const int colA = it[0], na = it[1], colB = it[2], nb = it[3], mb = t / nbB, nk = t - mb * nbB;
       const int ca0 = colA + min(16 * mb + g, na - 1), ca1 = colA + min(16 * mb + 8 + g, na - 1);
-      const int cb0 = colB + min(16 * nk + g, nb - 1), cb1 = colB + min(16 * nk + 8 + g, nb - 1);
+      const int xcol = it[5], ib0 = min(16 * nk + g, nb - 1), ib1 = min(16 * nk + 8 + g, nb - 1);
+      const int cb0 = (xcol >= 0 && ib0 == nb - 1) ? xcol : colB + ib0, cb1 = (xcol >= 0 && ib1 == nb - 1) ? xcol : colB + ib1;
       double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
       const bool hiA = na - 16 * mb > 8, hiB = nb - 16 * nk > 8;  // second 8-row / 8-column tile in use (warp-uniform)
 #pragma unroll 2
@@ -455,24 +456,25 @@ struct K {
   // ------------------------------------------------------------------------------------------------
   __device__ __forceinline__ unsigned smem_u32(const void* p) const { return (unsigned)__cvta_generic_to_shared(p); }
 
-  // (Re)initialises the panel pipeline for `ncons` consumer warps. Must be called by all threads; no copy may be in flight.
-  __device__ void pipe_setup(int ncons) {
-    if (ncons == pipe_ncons) return;
-    __syncthreads();
+  // Initialises the panel pipeline ONCE per kernel: full barriers expect the producer's arrive (+ the copy's bytes), empty
+  // barriers expect one arrive from EVERY consumer warp (RBO_NCONS) for every chunk, whether or not the warp has columns to
+  // work on in that pass. The barriers are never re-initialised, so there is no invalidate / init window to get wrong and the
+  // running chunk count qglob is identical in all threads by construction. Call from all threads before the first pass.
+  __device__ void pipe_init() {
     if (tid == 0) {
       for (int i = 0; i < RBO_NSTAGE; ++i) {
-        if (pipe_ncons != 0) {
-          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&mbar[i])));
-          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&mbar[RBO_NSTAGE + i])));
-        }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[i])));                           // full: producer + tx bytes
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[RBO_NSTAGE + i])), "r"(ncons));  // empty: one arrive per consumer warp
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[i])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[RBO_NSTAGE + i])), "r"(RBO_NCONS) : "memory");
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    pipe_ncons = ncons;
     qglob = 0;
     __syncthreads();
+  }
+  __device__ void pipe_fini() {  // all passes done: release the barrier objects
+    __syncthreads();
+    if (tid == 0)
+      for (int i = 0; i < 2 * RBO_NSTAGE; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&mbar[i])) : "memory");
   }
   __device__ __forceinline__ void chunk_issue(unsigned q, const double* src, int ndoubles) {  // one thread
     const unsigned st = q % RBO_NSTAGE, mb = smem_u32(&mbar[st]), dst = smem_u32(stage + (size_t)st * RBO_CHUNK_K * RBO_LP);
@@ -505,7 +507,7 @@ struct K {
       if (ok) return;
     }
     if (atomicExch(P.work_counter + 1, 1) == 0) {
-      P.work_counter[4] = 2; P.work_counter[5] = (int)q; P.work_counter[6] = warp; P.work_counter[7] = pipe_ncons; P.work_counter[8] = blockIdx.x;
+      P.work_counter[4] = 2; P.work_counter[5] = (int)q; P.work_counter[6] = warp; P.work_counter[7] = RBO_NCONS; P.work_counter[8] = blockIdx.x;
     }
   }
   __device__ __forceinline__ void empty_arrive(unsigned q) {
@@ -592,7 +594,6 @@ struct K {
     const unsigned chunks_per_pass = (unsigned)(nb * (nb + 1) / 2);
     const int ncons = min(ngroups, GPB) * NRQ;  // consumer warps of this pass: warps 0 .. ncons-1
     AUX_T(ts0_);
-    pipe_setup(ncons);
     AUX_ADD(0, ts0_);
 #ifdef RBO_PHASE_TIMERS
     if (tid == 0) atomicAdd(&g_aux_cycles[(FWD ? 0 : 8) + 6], 1ull);
@@ -615,14 +616,14 @@ struct K {
       __syncwarp();
       return;
     }
-    if (warp >= ncons) return;  // not part of this pass: free for other work until the caller's next __syncthreads
+    const bool part = warp < ncons;  // warps beyond take no columns in this pass but still consume (wait + release) every chunk
     // ---------------- consumer warps ----------------
     const int g = lane >> 2, tg = lane & 3;
     const int gl = warp / NRQ, rq = warp - gl * NRQ;  // group slot within the batch, row quarter
     unsigned q = qglob;
     for (int bt = 0; bt < nbatch; ++bt) {
       const int group = bt * GPB + gl;
-      const bool wact = group < ngroups;  // warp-uniform (false only in the last batch)
+      const bool wact = part && group < ngroups;  // warp-uniform
       // column offsets: cB for the B fragment (column g), c0/c1 for the C fragment (columns 2 tg, 2 tg + 1)
       const int i0 = 8 * group;
       const bool vB = wact && i0 + g < ncols, v0 = wact && i0 + 2 * tg < ncols, v1 = wact && i0 + 2 * tg + 1 < ncols;
@@ -753,7 +754,12 @@ struct K {
     const int nout_pre = np * q1;
     double* dmu = sm + pl.sdmu + sl * d; double* dsig = sm + pl.sdsig + sl * d; double* ga = sm + pl.sga + sl * d;
     double* Ht = sm + pl.sHt + sl * dd; double* Href = sm + pl.sHref + sl * dd; double* gh = sm + pl.sgh + sl * 8;
-    auto pre = [&](int e) { double s = 0.0; for (int r = 0; r < RSpre; ++r) s += ppre[(size_t)r * nout_pre + aidx * q1 + e]; return s; };
+    auto pre = [&](int e) {
+      double s = 0.0;
+      if (RSpre < 0) { for (int r = 0; r < RS1; ++r) s += p1[(size_t)r * nout1 + e * (-RSpre) + q1]; }  // V_e . u from the fused product
+      else for (int r = 0; r < RSpre; ++r) s += ppre[(size_t)r * nout_pre + aidx * q1 + e];
+      return s;
+    };
     auto one = [&](int e) { double s = 0.0; for (int r = 0; r < RS1; ++r) s += p1[(size_t)r * nout1 + e]; return s; };
     auto gramf = [&](int p, int q) { double s = 0.0; for (int r = 0; r < RSg; ++r) s += pg[(size_t)r * noutg + goff + p * gld + q]; return s; };
     auto hes = [&](int which, int e) { double s = 0.0; const int RS = which ? RShw : RShc; for (int r = 0; r < RS; ++r) s += phess[((size_t)(r * np + aidx) * 2 + which) * (T2 + 1) + e]; return s; };
@@ -960,6 +966,7 @@ struct K {
       PT_MARK(9);
       fill_columns(nact, pt, cb);
       for (int i = tid; i < nact * q1; i += RBO_THREADS) { int s = i / q1; colidx[i] = alist[s] * P.CS + (i - s * q1); }
+#if RBO_OVERLAP
       for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS, q1, CCOL, 1, s * q1);  // mu = kx.c, grad mu = grad_kx c (rbs.jl:513-514)
       __syncthreads();
       PT_MARK(0);
@@ -968,6 +975,12 @@ struct K {
       colprod(nact, nact * q1, sm + pl.ppre, RSpre);
       __syncthreads();  // the solve below overwrites the raw columns in place
       PT_MARK(1);
+#else
+      // mu = kx.c = (L^-1 kx).(L^-1 y) = v0.u and grad mu = V_g' u (rbs.jl:513-514) ride along with the Gram product after the solve
+      const int nbq = nblk16(q1), RSpre = 0;
+      __syncthreads();
+      PT_MARK(0);
+#endif
       tri_solve<true>(nact * q1, nf);
 #if RBO_OVERLAP
       for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS, 1, alist[s] * P.CS, q1, s * q1);  // |v0|^2, V_p.v0
@@ -1005,11 +1018,12 @@ struct K {
       __syncthreads();
       PT_MARK(5);
 #else
-      for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS, q1, alist[s] * P.CS, q1, s * q1 * q1);  // |v0|^2, V_p.v0, V_p.V_q
+      const int q2 = q1 + 1;  // B columns: the slot's q1 solved columns and u
+      for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS, q1, alist[s] * P.CS, q2, s * q1 * q2, UCOL);  // |v0|^2, V_p.v0, V_p.V_q | V_p.u
       __syncthreads();
       PT_MARK(2);
-      const int RS1 = choose_rs(nact * nbq * nbq), RSg = RS1;
-      colprod(nact, nact * q1 * q1, sm + pl.ppost, RS1);
+      const int RS1 = choose_rs(nact * nbq * nblk16(q2)), RSg = RS1;
+      colprod(nact, nact * q1 * q2, sm + pl.ppost, RS1);
       for (int i = tid; i < nact; i += RBO_THREADS) colidx[i] = alist[i] * P.CS;
       __syncthreads();
       PT_MARK(3);
@@ -1028,7 +1042,7 @@ struct K {
 #if RBO_OVERLAP
         assemble_warp(sl, s, nact, RSpre, sm + pl.ppost1 + s * q1, nact * q1, RS1, sm + pl.ppost, nact * d * d, s * d * d, d, RSg, RShc, RShw, misc[1]);
 #else
-        assemble_warp(sl, s, nact, RSpre, sm + pl.ppost + s * q1 * q1, nact * q1 * q1, RS1, sm + pl.ppost, nact * q1 * q1, s * q1 * q1 + q1 + 1, q1, RSg, RShc, RShw, misc[1]);
+        assemble_warp(sl, s, nact, -q2, sm + pl.ppost + s * q1 * q2, nact * q1 * q2, RS1, sm + pl.ppost, nact * q1 * q2, s * q1 * q2 + q2 + 1, q2, RSg, RShc, RShw, misc[1]);
 #endif
 #ifdef RBO_PHASE_TIMERS
         long long ta_ = clock64();
@@ -1088,6 +1102,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
   double* misc = k.misc;  // misc[0] best f, misc[1] fstar, misc[2..7] scalars, misc[8..] scratch
   int* si = k.si;
   k.build_tables();
+  k.pipe_init();
   for (int i = tid; i < NR * RP; i += RBO_THREADS) k.V[i] = 0.0;  // rows beyond the fantasy block are read (times exact zeros of L0's padding) but never written
   if (P.xsm) for (int i = tid; i < d * N8; i += RBO_THREADS) k.Xs[(i / N8) * P.XP + (i % N8)] = __ldg(P.Xb + i);
   __syncthreads();
@@ -1103,7 +1118,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
     for (int i = tid; i < (N8 + RBO_MAXFAN) * 8; i += RBO_THREADS) k.Fp[i] = 0.0;
     for (int i = tid; i < 64; i += RBO_THREADS) k.G[i] = ((i >> 3) == (i & 7)) ? 1.0 : 0.0;
     for (int i = tid; i < NR; i += RBO_THREADS) { double c = (i < N8) ? __ldg(P.c0 + i) : 0.0; k.cst[i] = c; k.V[(size_t)i * RP + k.CCOL] = c; }
-    for (int i = tid; i < NR; i += RBO_THREADS) k.u[i] = (i < N8) ? __ldg(P.u0 + i) : 0.0;
+    for (int i = tid; i < NR; i += RBO_THREADS) { double u0 = (i < N8) ? __ldg(P.u0 + i) : 0.0; k.u[i] = u0; k.V[(size_t)i * RP + k.UCOL] = u0; }
     __syncthreads();
     if (tid < 8) k.Fp[(size_t)(N8 + tid) * 8 + tid] = 1.0;  // inverse of the identity fantasy block
     if (tid == 0) { misc[1] = P.ymin_base; si[I_TSTATUS] = RBO_TRAJ_OK; }
@@ -1225,6 +1240,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
             for (int rr = 0; rr < 8; ++rr) k.Fp[(size_t)(N8 + cc) * 8 + rr] = col[rr];
           }
           k.u[N8 + r] = (yv - misc[5]) / lrr;
+          k.V[(size_t)(N8 + r) * RP + k.UCOL] = k.u[N8 + r];  // the inner solves read u from its column
         }
         __syncthreads();
         {
@@ -1474,6 +1490,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
     PT_MARK(11);
     if (tid == 0 && P.status) P.status[m] = si[I_TSTATUS];
   }
+  k.pipe_fini();
 }
 
 // ----------------------------------------------------------------------------------------------------
