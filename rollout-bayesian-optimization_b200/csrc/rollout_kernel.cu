@@ -523,15 +523,25 @@ struct K {
   // buf: staged chunk, k-major with pitch RBO_LP, already offset to the warp's first row tile; vrow0: V row of chunk-relative
   // k = 0; cB: this lane's B-fragment column offset.
   template <int MTW>
-  __device__ __forceinline__ void mma_chunk(const double* buf, const double* vrow0, int cB, int g, int tg, double (*c)[2]) const {
+  __device__ __forceinline__ void mma_chunk(const double* buf, const double* vrow0, int cB, int g, int tg, double (*c)[2], int nt) const {
     const int RP = P.RP;
     const double* vp = vrow0 + (size_t)tg * RP + cB;
     const double* ap = buf + (size_t)tg * RBO_LP + g;
+    if (nt >= MTW) {
 #pragma unroll
-    for (int kt = 0; kt < RBO_CHUNK_K / 4; ++kt) {
-      const double b = vp[(size_t)(4 * kt) * RP];
+      for (int kt = 0; kt < RBO_CHUNK_K / 4; ++kt) {
+        const double b = vp[(size_t)(4 * kt) * RP];
 #pragma unroll
-      for (int mt = 0; mt < MTW; ++mt) dmma(c[mt][0], c[mt][1], ap[4 * kt * RBO_LP + 8 * mt], b);
+        for (int mt = 0; mt < MTW; ++mt) dmma(c[mt][0], c[mt][1], ap[4 * kt * RBO_LP + 8 * mt], b);
+      }
+    } else {  // last block row: only the row tiles below N8 exist (the fantasy rows have their own panel); nt is warp-uniform
+#pragma unroll
+      for (int kt = 0; kt < RBO_CHUNK_K / 4; ++kt) {
+        const double b = vp[(size_t)(4 * kt) * RP];
+#pragma unroll
+        for (int mt = 0; mt < MTW; ++mt)
+          if (mt < nt) dmma(c[mt][0], c[mt][1], ap[4 * kt * RBO_LP + 8 * mt], b);
+      }
     }
   }
   __device__ __forceinline__ void group_sync(int NRQ, int group) const {  // the NRQ warps that share a column group
@@ -684,12 +694,13 @@ struct K {
           const double* buf = stage + (size_t)(q % RBO_NSTAGE) * RBO_CHUNK_K * RBO_LP + rofs;
           AUX_T(tm0_);
           if (wact) {
+            const int nt = (N8 - rb - rofs + 7) >> 3;  // row tiles of this warp that lie below N8 (<= 0: none)
             if (cc < nc - 1) {
               const int krow0 = (FWD ? 0 : rb + RBO_BR) + cc * RBO_CHUNK_K;  // V row of the first k of this chunk
-              mma_chunk<MTW>(buf, V + (size_t)krow0 * RP, cB, g, tg, c);
+              mma_chunk<MTW>(buf, V + (size_t)krow0 * RP, cB, g, tg, c, nt);
             } else {
               // last chunk of the panel = diagonal block of the inverse applied to the panel's own right-hand-side rows
-              mma_chunk<MTW>(buf, V + (size_t)rb * RP, cB, g, tg, c);
+              mma_chunk<MTW>(buf, V + (size_t)rb * RP, cB, g, tg, c, nt);
               AUX_T(td0_);
               group_sync(NRQ, gl);  // every warp of the group has read the right-hand-side rows
 #pragma unroll
