@@ -10,7 +10,7 @@ struct SmemPlan {
   int sx, sxt, sg, sH, sA, sp;               // per slot: x, trial x, gradient, Hessian, Cholesky scratch, step
   int sHt, sHref, sga, sdmu, sdsig, sgh;     // per slot: trial Hessian (-H alpha), reference H alpha, grad alpha, grad mu, grad sigma, scalars
   int sf, slam, spred, shs;                  // per slot scalars
-  int ppre, ppost, ppost1, phess;            // partial sums of the row reductions
+  int ppre, ppost, phess;                    // partial sums of the row reductions
   int bestx, misc, adj;                      // [d] best candidate ; scalar/scratch area ; adjoint duals
   int pairs, tbl, ints;                      // int areas (in doubles)
   int total;                                 // total doubles
@@ -97,7 +97,6 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.sf = take(W); p.slam = take(W); p.spred = take(W); p.shs = take(W);
   p.ppre = take(RSmax * W * q1);
   p.ppost = take(RSmax * NPmax);
-  p.ppost1 = take(0 * RSmax * W * q1);  // only the (disabled) overlap variant of the inner solve uses it
   p.phess = take(RSh * W * 2 * (T2 + 1));
   p.bestx = take(d);
   p.misc = take(64 + 2 * q1 * q1 + 2 * q1);

@@ -17,9 +17,6 @@
 //     perturbation columns (rbs.jl:633-764) are pushed into the right-hand sides of the earlier duals.
 #include "rbo_kernel.cuh"
 
-#ifndef RBO_OVERLAP
-#define RBO_OVERLAP 0  // 1: run the backward solve concurrently with the Gram / c-weighted Hessian sums (no gain measured on C3)
-#endif
 
 namespace rbo {
 
@@ -445,14 +442,7 @@ struct K {
   }
 
   // ------------------------------------------------------------------------------------------------
-  // Triangular solves of `ncols` (<= RBO_THREADS) columns of V (indices in colidx[]) against L = [L0 0; F G]:
-  // FWD: V <- L^-1 V, else V <- L^-T V.
-  //  * L0 lives in global memory as 8-row panels (pitch RBO_LP doubles per k, 8x8 diagonal blocks pre-inverted). The
-  //    panels are streamed ONCE per solve into a 3-stage shared-memory ring with TMA bulk copies
-  //    (cp.async.bulk + mbarrier complete_tx), issued two chunks ahead by thread 0; every warp consumes the same chunk.
-  //  * A group of KS adjacent lanes owns one column and splits the k-range of every panel; partial sums are combined
-  //    with xor-shuffles, the diagonal step is a small mat-vec with the inverted block.
-  //  * The fantasy rows (<= 8, per trajectory) are one more panel that already sits in shared memory.
+  // Panel pipeline: TMA bulk copies of the packed L0^-1 chunks into a shared-memory ring (see tri_solve below).
   // ------------------------------------------------------------------------------------------------
   __device__ __forceinline__ unsigned smem_u32(const void* p) const { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -574,15 +564,16 @@ struct K {
   __device__ __forceinline__ void c_to_b(double c0, double c1, int g, int tg, double& b0, double& b1) const { rbo::c_to_b(c0, c1, g, tg, b0, b1); }
   __device__ void bwd_direct(int ncols, int nfan) { rbo::bwd_direct(V, Fp, colidx, P.Lbf, P.RP, P.N8, P.nb32, ncols, nfan, warp, lane); }
 
-  // Triangular solves of `ncols` columns of V (indices in colidx[]) against L = [L0 0; F G]:
-  // FWD: V <- L^-1 V, else V <- L^-T V.
-  //  * L0 lives in global memory as 32-row panels, k-major (pitch RBO_LP), 32x32 diagonal blocks pre-inverted, cut into
-  //    uniform 32-k chunks. Warp RBO_NCONS is the producer: it streams the chunks ONCE per pass into a 3-stage
-  //    shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), throttled by "empty" mbarriers.
-  //  * Each consumer warp owns 8 columns (a warp-task) for all 32 rows of a panel and accumulates with FP64 tensor-core
-  //    tiles (mma.sync m8n8k4): per chunk 8 B-fragment loads, 32 A-fragment loads, 32 DMMA; no cross-warp dependency
-  //    exists inside a solve because a column never leaves its warp.
-  //  * The fantasy rows (<= 8, per trajectory) are one more panel that already sits in shared memory.
+  // "Triangular solves" of `ncols` columns of V (indices in colidx[]) against L = [L0 0; F G]: FWD: V <- L^-1 V, else V <- L^-T V.
+  //  * The host stores the EXPLICIT inverse of L0 as 32-row panels, k-major (pitch RBO_LP), cut into uniform 32-k chunks, so
+  //    a block row of the result is a plain product with right-hand-side rows: v_I = sum_{J<=I} Linv[I][J] b_J. The block rows
+  //    are visited in the order that overwrites a block only after its last use as input (descending for FWD).
+  //  * Warp RBO_NCONS is the producer: it streams the chunks ONCE per pass into a 3-stage shared-memory ring with TMA bulk
+  //    copies (cp.async.bulk + mbarrier complete_tx), throttled by "empty" mbarriers that every consumer warp releases.
+  //  * A column group = 8 columns; NRQ = 1, 2 or 4 warps share a group (32 / NRQ rows each) and accumulate with FP64
+  //    tensor-core tiles (mma.sync m8n8k4); they meet at a named barrier before the block row is overwritten.
+  //  * The fantasy rows (<= 8, per trajectory) are one more panel that already sits in shared memory (DMMA as well).
+  //  * The backward direction with few columns (the inner solve: one per start) takes bwd_direct() instead.
   template <bool FWD>
   __device__ void tri_solve(int ncols, int nfan) {
     if (ncols <= 0) return;
@@ -977,58 +968,11 @@ struct K {
       PT_MARK(9);
       fill_columns(nact, pt, cb);
       for (int i = tid; i < nact * q1; i += RBO_THREADS) { int s = i / q1; colidx[i] = alist[s] * P.CS + (i - s * q1); }
-#if RBO_OVERLAP
-      for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS, q1, CCOL, 1, s * q1);  // mu = kx.c, grad mu = grad_kx c (rbs.jl:513-514)
-      __syncthreads();
-      PT_MARK(0);
-      const int nbq = nblk16(q1);
-      const int RSpre = choose_rs(nact * nbq);
-      colprod(nact, nact * q1, sm + pl.ppre, RSpre);
-      __syncthreads();  // the solve below overwrites the raw columns in place
-      PT_MARK(1);
-#else
       // mu = kx.c = (L^-1 kx).(L^-1 y) = v0.u and grad mu = V_g' u (rbs.jl:513-514) ride along with the Gram product after the solve
-      const int nbq = nblk16(q1), RSpre = 0;
+      const int nbq = nblk16(q1);
       __syncthreads();
       PT_MARK(0);
-#endif
       tri_solve<true>(nact * q1, nf);
-#if RBO_OVERLAP
-      for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS, 1, alist[s] * P.CS, q1, s * q1);  // |v0|^2, V_p.v0
-      __syncthreads();
-      PT_MARK(2);
-      const int RS1 = choose_rs(nact * nbq);
-      colprod(nact, nact * q1, sm + pl.ppost1, RS1);
-      __syncthreads();
-      for (int i = tid; i < nact; i += RBO_THREADS) colidx[i] = alist[i] * P.CS;
-      for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS + 1, d, alist[s] * P.CS + 1, d, s * d * d);  // V_p.V_q
-      __syncthreads();
-      PT_MARK(3);
-      // w = L^-T v0 (rbs.jl:525) on the few warps the backward pass can use; meanwhile the other consumer warps do the
-      // reductions that do not need w: the Gram matrix of V_g and the c-weighted Hessian sums
-      const int nbd = nblk16(d);
-      const int ngb = (nact + 7) >> 3, nwb = min((ngb * 4 <= RBO_NCONS) ? ngb * 4 : ((ngb * 2 <= RBO_NCONS) ? ngb * 2 : ngb), RBO_NCONS);
-      const int nwo = RBO_NCONS - nwb;
-      const bool overlap = RBO_OVERLAP && nwo >= 2 * nact;  // enough spare warps for the other reductions
-      const int RSg = overlap ? choose_rs(nact * nbd * nbd, nwo) : choose_rs(nact * nbd * nbd);
-      const int RShc = overlap ? choose_rs(nact * nbd * (nbd + 1) / 2, nwo) : choose_rs(nact * nbd * (nbd + 1) / 2);
-      tri_solve<false>(nact, nf);
-      if (overlap) {
-        colprod(nact, nact * d * d, sm + pl.ppost, RSg, nwb, nwo);
-        hess_sums<1>(nact, pt, cb, cb, RShc, nwb, nwo);
-      }
-      __syncthreads();
-      PT_MARK(4);
-      const int RShw = choose_rs(nact * nbd * (nbd + 1) / 2);
-      if (overlap) {
-        hess_sums<2>(nact, pt, cb, cb, RShw);
-      } else {
-        colprod(nact, nact * d * d, sm + pl.ppost, RSg);
-        hess_sums<3>(nact, pt, cb, cb, RShw);  // RShc == RShw here
-      }
-      __syncthreads();
-      PT_MARK(5);
-#else
       const int q2 = q1 + 1;  // B columns: the slot's q1 solved columns and u
       for (int s = tid; s < nact; s += RBO_THREADS) set_item(s, alist[s] * P.CS, q1, alist[s] * P.CS, q2, s * q1 * q2, UCOL);  // |v0|^2, V_p.v0, V_p.V_q | V_p.u
       __syncthreads();
@@ -1046,15 +990,10 @@ struct K {
       hess_sums<3>(nact, pt, cb, cb, RShw);
       __syncthreads();
       PT_MARK(5);
-#endif
       // per-start logic: one warp per active slot
       for (int s = warp; s < nact; s += RBO_NWARPS) {
         const int sl = alist[s];
-#if RBO_OVERLAP
-        assemble_warp(sl, s, nact, RSpre, sm + pl.ppost1 + s * q1, nact * q1, RS1, sm + pl.ppost, nact * d * d, s * d * d, d, RSg, RShc, RShw, misc[1]);
-#else
         assemble_warp(sl, s, nact, -q2, sm + pl.ppost + s * q1 * q2, nact * q1 * q2, RS1, sm + pl.ppost, nact * q1 * q2, s * q1 * q2 + q2 + 1, q2, RSg, RShc, RShw, misc[1]);
-#endif
 #ifdef RBO_PHASE_TIMERS
         long long ta_ = clock64();
         if (tid == 0) atomicAdd(&g_phase_cycles[8], (unsigned long long)(ta_ - pt_t0));
