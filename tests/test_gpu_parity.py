@@ -256,9 +256,10 @@ def test_other_kernels_and_rules(pkg, orc, kernel, ktheta, rule, theta):
     assert fv >= 0.95, ev
 
 
-@pytest.mark.parametrize("d,N,h,S", [(1, 9, 2, 3), (20, 40, 1, 3), (31, 33, 1, 2), (4, 97, 7, 3)])
+@pytest.mark.parametrize("d,N,h,S", [(1, 9, 2, 3), (20, 40, 1, 3), (31, 33, 1, 2), (4, 97, 7, 3), (2, 300, 2, 3)])
 def test_dimension_extremes(pkg, orc, d, N, h, S):
-    """d = 1, d > 16 (more than one 16 x 16 output block), d = 31, the longest supported horizon and a ragged last panel."""
+    """d = 1, d > 16 (more than one 16 x 16 output block), d = 31, the longest supported horizon and a ragged last panel,
+    N > 256 (ten 32-row panels: the backward pass goes through the staged ring instead of the direct L2 path)."""
     M = 24
     sur, P, rn, starts, dd, lbs, ubs, x0 = custom_case(pkg, orc, d, N, h, M, S, "Matern52", (0.6 * np.sqrt(d),), "EI", (0.0,))
     ref = P.rollout()
