@@ -134,46 +134,38 @@ __device__ __noinline__ void bwd_direct(double* V, const double* Fp, const int* 
       const bool wact = warp < gpb * tpg && group < ngroups;
       int cB = 0, c0 = 0, c1 = 0; bool v0 = false, v1 = false;
       if (wact) cols(group, cB, c0, c1, v0, v1);
-      const int nA = wact ? nb - cls : 0;                                  // tiles of block row cls
-      const int ns = nA + ((wact && nb - 1 - cls != cls) ? cls + 1 : 0);   // ... plus those of block row nb-1-cls
       double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-      const double2* ap = nullptr; const double* vp = nullptr;
-      auto locate = [&](int s) {
-        const int hh = s >= nA, cc = hh ? s - nA : s, ib = hh ? nb - 1 - cls : cls, nc = nb - ib, rb = RBO_BR * ib;
-        const size_t chunk = (size_t)nb * ib - (size_t)ib * (ib - 1) / 2 + cc;
-        ap = reinterpret_cast<const double2*>(Lbf + (chunk * 4 + rq) * 256) + lane;
-        vp = V + (size_t)(((cc < nc - 1) ? rb + RBO_BR + cc * RBO_CHUNK_K : rb) + tg) * RP + cB;
-      };
-      auto compute = [&](const double2 (&A)[4], const double* v, bool hh) {
-        double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;
-#pragma unroll
-        for (int pp = 0; pp < 4; ++pp) {
-          dmma(e0, e1, A[pp].x, v[(size_t)(8 * pp) * RP]);
-          dmma(o0, o1, A[pp].y, v[(size_t)(8 * pp + 4) * RP]);
-        }
-        e0 += o0; e1 += o1;
-        if (hh) { acc[1][0] += e0; acc[1][1] += e1; } else { acc[0][0] += e0; acc[0][1] += e1; }
-      };
+      const int rp4 = 4 * RP, rp8 = 8 * RP;
       __syncthreads();  // fantasy-row update of the top rows / previous batch stored
-      double2 A0[4], A1[4];
-      const double *vq0 = nullptr, *vq1 = nullptr;
-      if (0 < ns) { locate(0); vq0 = vp;
 #pragma unroll
-        for (int pp = 0; pp < 4; ++pp) A0[pp] = __ldg(ap + 32 * pp); }
-      if (1 < ns) { locate(1); vq1 = vp;
+      for (int hh = 0; hh < 2; ++hh) {
+        const int ib = hh ? nb - 1 - cls : cls, rb = RBO_BR * ib;
+        // warp-uniform: the block row exists, is not visited twice, and this row quarter lies (partly) below N8
+        if (!wact || (hh && ib == cls) || rb + 8 * rq >= N8) continue;
+        const int nc = nb - ib, chunk0 = nb * ib - ib * (ib - 1) / 2;
+        const double2* ap = reinterpret_cast<const double2*>(Lbf) + (size_t)(chunk0 * 4 + rq) * 128 + lane;  // 128 double2 per tile, 512 per chunk
+        const double* vd = V + (rb + tg) * RP + cB;  // right-hand-side rows of block ib (used by the last, diagonal tile)
+        double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;  // two accumulator chains over the whole block row
+        double2 A[4], An[4];
 #pragma unroll
-        for (int pp = 0; pp < 4; ++pp) A1[pp] = __ldg(ap + 32 * pp); }
-      for (int s = 0; s < ns; s += 2) {
-        compute(A0, vq0, s >= nA);
-        if (s + 2 < ns) { locate(s + 2); vq0 = vp;
+        for (int pp = 0; pp < 4; ++pp) A[pp] = __ldg(ap + 32 * pp);
+        for (int cc = 0; cc < nc; ++cc) {
+          const double* v = (cc < nc - 1) ? vd + (RBO_BR + RBO_CHUNK_K * cc) * RP : vd;
+          if (cc + 1 < nc) {
 #pragma unroll
-          for (int pp = 0; pp < 4; ++pp) A0[pp] = __ldg(ap + 32 * pp); }
-        if (s + 1 < ns) {
-          compute(A1, vq1, s + 1 >= nA);
-          if (s + 3 < ns) { locate(s + 3); vq1 = vp;
+            for (int pp = 0; pp < 4; ++pp) An[pp] = __ldg(ap + 512 * (cc + 1) + 32 * pp);
+          }
 #pragma unroll
-            for (int pp = 0; pp < 4; ++pp) A1[pp] = __ldg(ap + 32 * pp); }
+          for (int pp = 0; pp < 4; ++pp) {
+            dmma(e0, e1, A[pp].x, v[pp * rp8]);
+            dmma(o0, o1, A[pp].y, v[pp * rp8 + rp4]);
+          }
+          if (cc + 1 < nc) {
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) A[pp] = An[pp];
+          }
         }
+        acc[hh][0] = e0 + o0; acc[hh][1] = e1 + o1;
       }
       __syncthreads();  // all right-hand-side rows of this batch have been read
       if (wact) {
