@@ -312,18 +312,31 @@ struct K {
       const int cb0 = (xcol >= 0 && ib0 == nb - 1) ? xcol : colB + ib0, cb1 = (xcol >= 0 && ib1 == nb - 1) ? xcol : colB + ib1;
       double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
       const bool hiA = na - 16 * mb > 8, hiB = nb - 16 * nk > 8;  // second 8-row / 8-column tile in use (warp-uniform)
+      // full 4-row steps without predicates, then at most one ragged step
+      const int step = 4 * RS * RP, nfull = nrows & ~3;
+      const double* row = V + (4 * rs + tg) * RP;
+      int j0 = 4 * rs;
 #pragma unroll 2
-      for (int j0 = 4 * rs; j0 < nrows; j0 += 4 * RS) {
-        const int j = j0 + tg;
-        const bool in = j < nrows;
-        const double* row = V + (size_t)(in ? j : 0) * RP;
-        const double a0 = in ? row[ca0] : 0.0, b0 = in ? row[cb0] : 0.0;
+      for (; j0 < nfull; j0 += 4 * RS, row += step) {
+        const double a0 = row[ca0], b0 = row[cb0];
         dmma(c00[0], c00[1], a0, b0);
-        if (hiB) { const double b1 = in ? row[cb1] : 0.0; dmma(c01[0], c01[1], a0, b1); }
+        if (hiB) dmma(c01[0], c01[1], a0, row[cb1]);
         if (hiA) {
-          const double a1 = in ? row[ca1] : 0.0;
+          const double a1 = row[ca1];
           dmma(c10[0], c10[1], a1, b0);
-          if (hiB) { const double b1 = in ? row[cb1] : 0.0; dmma(c11[0], c11[1], a1, b1); }
+          if (hiB) dmma(c11[0], c11[1], a1, row[cb1]);
+        }
+      }
+      if (j0 < nrows) {
+        const bool in = j0 + tg < nrows;
+        const double* rw = in ? row : V;
+        const double a0 = in ? rw[ca0] : 0.0, b0 = in ? rw[cb0] : 0.0;
+        dmma(c00[0], c00[1], a0, b0);
+        if (hiB) { const double b1 = in ? rw[cb1] : 0.0; dmma(c01[0], c01[1], a0, b1); }
+        if (hiA) {
+          const double a1 = in ? rw[ca1] : 0.0;
+          dmma(c10[0], c10[1], a1, b0);
+          if (hiB) { const double b1 = in ? rw[cb1] : 0.0; dmma(c11[0], c11[1], a1, b1); }
         }
       }
       double* o = dst + (size_t)rs * nout + it[4];
@@ -365,8 +378,7 @@ struct K {
       const int xst = P.xsm ? P.XP : P.N8;
       const int op0 = p0 * xst, op1 = p1 * xst, oq0 = q0 * xst, oq1 = q1_ * xst;
       const int nbase4 = P.N8 & ~3;
-      auto body = [&](int jj, bool in, double rp0, double rp1, double rq0, double rq1) {
-        const double* row = V + (size_t)jj * RP;
+      auto body = [&](const double* row, bool in, double rp0, double rp1, double rq0, double rq1) {
         const double aj = in ? row[colab] : 0.0, bj = in ? row[colab + 1] : 0.0;
         const double wj = (MASK & 2) ? row[colw] : 0.0, cj = (MASK & 1) ? row[CCOL] : 0.0;
         const double ca = cj * aj, wa = wj * aj;
@@ -389,28 +401,30 @@ struct K {
         }
       };
       int j0 = 4 * rs;
+      const int jstep = 4 * RS;
+      const double* row = V + (j0 + tg) * RP;
       if (P.xsm) {
+        const double* xs = Xs + j0 + tg;
 #pragma unroll 2
-        for (; j0 < nbase4; j0 += 4 * RS) {
-          const int j = j0 + tg;
-          const double rp0 = xp0 - Xs[op0 + j], rp1 = xp1 - Xs[op1 + j];
-          const double rq0 = diag ? rp0 : xq0 - Xs[oq0 + j], rq1 = diag ? rp1 : xq1 - Xs[oq1 + j];
-          body(j, true, rp0, rp1, rq0, rq1);
+        for (; j0 < nbase4; j0 += jstep, row += jstep * RP, xs += jstep) {
+          const double rp0 = xp0 - xs[op0], rp1 = xp1 - xs[op1];
+          const double rq0 = diag ? rp0 : xq0 - xs[oq0], rq1 = diag ? rp1 : xq1 - xs[oq1];
+          body(row, true, rp0, rp1, rq0, rq1);
         }
       } else {
+        const double* xs = P.Xb + j0 + tg;
 #pragma unroll 2
-        for (; j0 < nbase4; j0 += 4 * RS) {
-          const int j = j0 + tg;
-          const double rp0 = xp0 - __ldg(P.Xb + op0 + j), rp1 = xp1 - __ldg(P.Xb + op1 + j);
-          const double rq0 = diag ? rp0 : xq0 - __ldg(P.Xb + oq0 + j), rq1 = diag ? rp1 : xq1 - __ldg(P.Xb + oq1 + j);
-          body(j, true, rp0, rp1, rq0, rq1);
+        for (; j0 < nbase4; j0 += jstep, row += jstep * RP, xs += jstep) {
+          const double rp0 = xp0 - __ldg(xs + op0), rp1 = xp1 - __ldg(xs + op1);
+          const double rq0 = diag ? rp0 : xq0 - __ldg(xs + oq0), rq1 = diag ? rp1 : xq1 - __ldg(xs + oq1);
+          body(row, true, rp0, rp1, rq0, rq1);
         }
       }
-      for (; j0 < nrows; j0 += 4 * RS) {  // last base rows (N8 not a multiple of 4 never happens; kept general) and the fantasy rows
+      for (; j0 < nrows; j0 += jstep) {  // the fantasy rows
         const int j = j0 + tg;
         const bool in = j < nrows;
         const int jj = in ? j : 0;
-        body(jj, in, xp0 - xcoord(jj, p0), xp1 - xcoord(jj, p1), xq0 - xcoord(jj, q0), xq1 - xcoord(jj, q1_));
+        body(V + (size_t)jj * RP, in, xp0 - xcoord(jj, p0), xp1 - xcoord(jj, p1), xq0 - xcoord(jj, q0), xq1 - xcoord(jj, q1_));
       }
       bC += __shfl_xor_sync(FULL, bC, 1); bC += __shfl_xor_sync(FULL, bC, 2);
       bW += __shfl_xor_sync(FULL, bW, 1); bW += __shfl_xor_sync(FULL, bW, 2);
