@@ -312,10 +312,10 @@ def main():
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved_per_gpu, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_per_gpu / peak_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on the default workload
-                         # (C3, M = 16384, 1 GPU), from the ncu capture in profiles/r1b_dram_fullM.csv: 15 794 688 + 2 006 784 B --
+                         # (C3, M = 16384, 1 GPU), from the ncu capture in profiles/r1f_dram_fullM.csv: 15 340 032 + 402 432 B --
                          # i.e. the normals, dual directions and outputs once; the rest stays in L2 / shared memory
-                         "traffic": 17801472 if (args.workload == "C3" and args.M is None and world == 1) else None,
-                         "traffic_unit": "bytes per launch (ncu, profiles/r1b_dram_fullM.csv)",
+                         "traffic": 15742464 if (args.workload == "C3" and args.M is None and world == 1) else None,
+                         "traffic_unit": "bytes per launch (ncu, profiles/r1f_dram_fullM.csv)",
                          "kernel": "rbo_rollout_kernel", "kernel_ms": kernel_ms,
                          "flops_per_launch": acct[0] / world, "flops_executed_per_launch": acct[1] / world,
                          "frac_executed": acct[1] / world / (kernel_ms * 1e-3) / 1e12 / peak_tf,
