@@ -42,7 +42,7 @@ struct DevProblem {
   const double* yb;      // [N]
   const double* c0;      // [N8] base coefficients K^-1 y (pad 0)
   const double* u0;      // [N8] L0^-1 y (pad 0)
-  const double* Lf;      // forward panels of L0 with inverted diagonal blocks
+  const double* Lf;      // forward panels of L0^-1, k-major (staged through the shared-memory ring)
   const double* Lb;      // backward (transposed) panels of L0^-1, k-major (staged through the shared-memory ring)
   const double* Lbf;     // the same panels in mma A-fragment order (read straight from L2 by the few-column backward pass)
   const double* rn;      // [M][(d+1)][hp1] column-major (sample fastest)

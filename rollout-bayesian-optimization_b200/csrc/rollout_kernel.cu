@@ -545,21 +545,6 @@ struct K {
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * NRQ) : "memory");
   }
 
-  // ---- 8-row fantasy panel (shared memory, pitch 8): 4 lanes own one column and split k ----
-  __device__ __forceinline__ void fan_rows(const double* pan, int kend, int part, const double* vcol, double acc[8]) const {
-    const int RP = P.RP;
-#pragma unroll 2
-    for (int k = part; k < kend; k += 4) {
-      const double v = vcol[(size_t)k * RP];
-      const double2* lp = reinterpret_cast<const double2*>(pan + (size_t)k * 8);
-      const double2 l0 = lp[0], l1 = lp[1], l2 = lp[2], l3 = lp[3];
-      acc[0] = fma(l0.x, v, acc[0]); acc[1] = fma(l0.y, v, acc[1]);
-      acc[2] = fma(l1.x, v, acc[2]); acc[3] = fma(l1.y, v, acc[3]);
-      acc[4] = fma(l2.x, v, acc[4]); acc[5] = fma(l2.y, v, acc[5]);
-      acc[6] = fma(l3.x, v, acc[6]); acc[7] = fma(l3.y, v, acc[7]);
-    }
-  }
-
   template <bool FWD>
   __device__ __forceinline__ const double* pan_ptr(int ib) const {  // global address of panel ib (see rbo_set_surrogate)
     const size_t chunk = (size_t)RBO_LP * RBO_BR;
