@@ -389,3 +389,59 @@ def test_simulate_trajectory_ghq_free_running(pkg, orc):
     with pytest.raises(pkg.RboError):  # depth < horizon + 1 (observables.jl:55 assertion)
         pkg.simulate_trajectory_ghq(T, tp, inner_solve_xstarts=starts, resolutions=res2, nodes=nodes, weights=weights,
                                     indices=pkg.generate_indices(5, wl.h))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Committed fixtures (tests/golden/): the CUDA path against stored vectors, no oracle call at test time
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["mc_hartmann6", "mc_gp2d", "ghq_hartmann6"])
+def test_golden_fixture_teacher_forced(pkg, name):
+    import os
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    h, N = int(f["h"]), f["X"].shape[1]
+    d, M = f["X"].shape[0], f["values"].shape[0]
+    sur = pkg.Surrogate(pkg.Matern52([float(f["ell"])]), f["X"], f["y"], capacity=N + h + 1, decision_rule=pkg.EI(), σn2=float(f["sigma_n2"]))
+    eng = pkg.RolloutEngine(0)
+    try:
+        eng.set_surrogate(pkg.FantasySurrogate(sur, h))
+        ghq = "gh_nodes" in f.files
+        if ghq:
+            eng.set_quadrature(f["gh_nodes"], f["gh_weights"])
+        else:
+            eng.set_normals(f["rn"])
+        eng.set_starts(f["starts"])
+        vals, gx, gt = np.zeros(M), np.zeros((d, M), order="F"), np.zeros((1, M), order="F")
+        bi, gc, st = np.zeros(M, np.int32), np.zeros(M, np.int32), np.zeros(M, np.int32)
+        eng.rollout(f["x0"], f["theta"], f["lbs"], f["ubs"], h, float(f["fmini"]), vals, gx, gt, dual_dirs=f["dual_dirs"],
+                    x_forced=np.asfortranarray(f["xs"][:, 1:, :]), best_index=bi, grad_case=gc, status=st, gauss_hermite=ghq)
+        tape = eng.tape(h)
+    finally:
+        eng.close()
+    assert np.all(st == 0) and np.array_equal(bi, f["best_index"]) and np.array_equal(gc, f["grad_case"])
+    assert relerr(tape["ys"], f["ys"]) < 1e-9 and relerr(tape["gys"], f["gys"]) < 1e-8
+    assert relerr(vals, f["values"], floor=max(np.abs(f["values"]).max(), 1e-300)) < 1e-9
+    gscale = np.maximum(np.abs(f["grad_x"]).max(axis=0, keepdims=True), 1e-9)
+    assert np.max(np.abs(gx - f["grad_x"]) / gscale) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["mc_hartmann6", "mc_gp2d"])
+def test_golden_fixture_free_running(pkg, name):
+    """Same fixtures, the kernel's own inner solve: the stored x-path (the oracle's solve) must be reproduced."""
+    import os
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    h, N = int(f["h"]), f["X"].shape[1]
+    d, M = f["X"].shape[0], f["values"].shape[0]
+    sur = pkg.Surrogate(pkg.Matern52([float(f["ell"])]), f["X"], f["y"], capacity=N + h + 1, decision_rule=pkg.EI(), σn2=float(f["sigma_n2"]))
+    eng = pkg.RolloutEngine(0)
+    try:
+        eng.set_surrogate(pkg.FantasySurrogate(sur, h))
+        eng.set_normals(f["rn"])
+        eng.set_starts(f["starts"])
+        vals, gx, gt = np.zeros(M), np.zeros((d, M), order="F"), np.zeros((1, M), order="F")
+        eng.rollout(f["x0"], f["theta"], f["lbs"], f["ubs"], h, float(f["fmini"]), vals, gx, gt, dual_dirs=f["dual_dirs"])
+        tape = eng.tape(h)
+    finally:
+        eng.close()
+    fx, ex = frac_within(tape["xs"], f["xs"], 1e-7, 1.0)
+    fv, ev = frac_within(vals, f["values"], 1e-8, 1.0)
+    assert fx >= 0.97 and fv >= 0.97, (ex, ev)

@@ -265,3 +265,24 @@ def test_gauss_hermite_observable_formula(pkg, orc):
             assert np.allclose(gy, r["gys"][:, k, m], rtol=1e-9, atol=1e-12)
         t = int(np.argmin(ys))
         assert np.isclose(r["values"][m], weights[t, m] * max(fmini - min(ys), 0.0) / np.sqrt(np.pi), rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["mc_hartmann6", "mc_gp2d", "ghq_hartmann6"])
+def test_oracle_reproduces_golden(orc, name):
+    """The committed fixtures (tests/golden/gen_golden.py: oracle output cross-checked with the numpy restatement) pin the
+    oracle against silent drift: free-running rollout from the stored inputs must reproduce every stored output."""
+    import os
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    kw = {}
+    if "gh_nodes" in f.files:
+        kw = dict(gh_nodes=f["gh_nodes"], gh_weights=f["gh_weights"])
+    P = orc.OracleProblem(f["X"], f["L"], f["y"], f["c"], f["x0"], f["lbs"], f["ubs"], f["rn"], f["starts"], h=int(f["h"]), kernel="matern52",
+                          ktheta=(float(f["ell"]),), rule="EI", theta=f["theta"], sigma_n2=float(f["sigma_n2"]), fmini=float(f["fmini"]), mode=1,
+                          dual_dirs=f["dual_dirs"], **kw)
+    r = P.rollout()
+    assert np.all(r["status"] == 0)
+    assert np.array_equal(r["best_index"], f["best_index"]) and np.array_equal(r["grad_case"], f["grad_case"])
+    for key, tol in (("xs", 1e-10), ("ys", 1e-10), ("gys", 1e-9), ("values", 1e-10), ("alphas", 1e-10)):
+        assert relerr(r[key], f[key]) < tol, key
+    gscale = np.maximum(np.abs(f["grad_x"]).max(axis=0, keepdims=True), 1e-9)
+    assert np.max(np.abs(r["grad_x"] - f["grad_x"]) / gscale) < 1e-7
