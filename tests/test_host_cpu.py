@@ -100,3 +100,17 @@ def test_finalize_sums_merges_shards(pkg):
     assert np.isclose(m.value, allA[0].mean()) and np.isclose(s.value, allA[0].std(ddof=1))
     assert np.allclose(gm, allA[1:1 + d].mean(axis=1)) and np.allclose(gs, allA[1:1 + d].std(axis=1, ddof=1))
     assert np.allclose(tm, allA[1 + d:].mean(axis=1)) and np.allclose(ts, allA[1 + d:].std(axis=1, ddof=1))
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU restatement on host cores) needs no GPU and prints the contract's JSON line."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "16"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "trajectories/s" and line["value"] > 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
