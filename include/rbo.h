@@ -140,6 +140,15 @@ int rbo_rollout(rbo_handle* h, const double* x0, const double* theta, int ntheta
                 double* values, double* grad_x, double* grad_theta, int32_t* best_index, int32_t* grad_case,
                 int32_t* status, rbo_summary* summary);
 
+/* The estimator at n_x0 starting points in ONE launch (the batch of stochastic-ascent restarts of
+ * the reference's outer loop, utils.jl:235-265 / the old driver's --batch-size): trajectory (b, m) starts at x0s[:, b] and uses
+ * sample m of the resident normals (common random numbers across the batch, as a serial loop over simulate_trajectory_mc
+ * with the same TrajectoryParameters would). x0s: d x n_x0; dual_dirs: d x h x m_count (shared by the batch) or NULL;
+ * values: m_count x n_x0, grad_x: d x m_count x n_x0, grad_theta: ntheta x m_count x n_x0, status: m_count x n_x0
+ * (column-major, sample index fastest within a starting point). Identical, bit for bit, to n_x0 calls of rbo_rollout. */
+int rbo_rollout_batch(rbo_handle* h, const double* x0s, int n_x0, const double* theta, int ntheta, const double* lbs, const double* ubs, int horizon,
+                      double fmini, int mode, const double* dual_dirs, double* values, double* grad_x, double* grad_theta, int32_t* status,
+                      rbo_summary* summary);
 /* Same computation, results left on the device (no per-trajectory D2H): only x0 (d doubles) goes in and the
  * partial sums come out through rbo_get_partial_sums. Used by the SGA loop and by bench.py's device-resident
  * timing. dual_dirs_device / x_forced_device are device pointers or NULL. */

@@ -473,6 +473,19 @@ class RolloutEngine:
                                                iptr(best_index), iptr(grad_case), iptr(status), C.byref(s)))
         return s
 
+    def rollout_batch(self, x0s, theta, lbs, ubs, horizon, fmini, values, grad_x=None, grad_theta=None, dual_dirs=None, status=None):
+        """x0s: d x B; values: M x B; grad_x: d x M x B; grad_theta: ntheta x M x B (column-major)."""
+        x0s = np.asfortranarray(x0s, dtype=np.float64); theta = np.ascontiguousarray(theta, dtype=np.float64)
+        lbs = np.ascontiguousarray(lbs, dtype=np.float64); ubs = np.ascontiguousarray(ubs, dtype=np.float64)
+        mode = 1 if (grad_x is not None and grad_theta is not None) else 0
+        if dual_dirs is not None:
+            dual_dirs = np.asfortranarray(dual_dirs, dtype=np.float64)
+        s = Summary()
+        self.handle.check(self.lib.rbo_rollout_batch(self.handle.h, dptr(x0s), x0s.shape[1], dptr(theta), len(theta), dptr(lbs), dptr(ubs), horizon,
+                                                     float(fmini), mode, dptr(dual_dirs), dptr(values), dptr(grad_x), dptr(grad_theta), iptr(status),
+                                                     C.byref(s)))
+        return s
+
     def rollout_device(self, x0, theta, lbs, ubs, horizon, fmini, mode, dual_dirs_ptr=None, want_summary=False):
         x0 = np.ascontiguousarray(x0, dtype=np.float64); theta = np.ascontiguousarray(theta, dtype=np.float64)
         lbs = np.ascontiguousarray(lbs, dtype=np.float64); ubs = np.ascontiguousarray(ubs, dtype=np.float64)
@@ -620,6 +633,44 @@ def simulate_trajectory_ghq(T, tp, *, inner_solve_xstarts, resolutions, nodes, w
     mgx, sgx = _mean_std_rows(spatial_gradients_container)
     mgt, sgt = _mean_std_rows(hyperparameter_gradients_container)
     return ExpectedTrajectoryOutput(float(μ[0]), float(σ[0]), mgx, sgx, mgt, sgt, summary=summary)
+
+
+def simulate_trajectory_mc_batch(T, tp, x0s, *, inner_solve_xstarts, dual_directions=None, want_gradients=True, device=0):
+    """simulate_trajectory_mc (rollout.jl:279-340) at every column of x0s (d x B) in ONE launch: what a serial loop
+    `for x0 in eachcol(x0s); set_starting_point!(tp, x0); simulate_trajectory_mc(T, tp; ...)` computes (same normals for every
+    starting point, as the shared TrajectoryParameters imply). Returns a list of ExpectedTrajectoryOutput, one per column."""
+    x0s = np.asfortranarray(x0s, dtype=np.float64)
+    d, h, M, B = len(tp.x0), tp.horizon, tp.mc_iters, x0s.shape[1]
+    nth = len(tp.θ)
+    vals = np.zeros((M, B), order="F")
+    gx = np.zeros((d, M, B), order="F") if want_gradients else None
+    gt = np.zeros((nth, M, B), order="F") if want_gradients else None
+    status = np.zeros((M, B), np.int32, order="F")
+    if want_gradients and dual_directions is None and h > 0:
+        dual_directions = np.asfortranarray(np.random.rand(d, h, M))
+    eng = RolloutEngine(device)
+    try:
+        eng.set_surrogate(T.fs)
+        eng.set_normals(tp.rnstream_sequence)
+        eng.set_starts(inner_solve_xstarts)
+        fmini = float(np.min(get_observations(T.s)))
+        summary = eng.rollout_batch(x0s, tp.θ, tp.spatial_lbs, tp.spatial_ubs, h, fmini, vals, gx, gt,
+                                    dual_dirs=dual_directions if want_gradients else None, status=status)
+    finally:
+        eng.close()
+    if np.any(status):
+        b, m = np.argwhere(status.T != 0)[0]
+        raise RboError(f"starting point {b + 1}, sample {m + 1}: trajectory failed with status {int(status[m, b])}")
+    out = []
+    for b in range(B):
+        μ, σ = _mean_std_rows(vals[:, b])
+        if not want_gradients:
+            out.append(ExpectedTrajectoryOutput(float(μ[0]), float(σ[0]), summary=summary))
+            continue
+        mgx, sgx = _mean_std_rows(gx[:, :, b])
+        mgt, sgt = _mean_std_rows(gt[:, :, b])
+        out.append(ExpectedTrajectoryOutput(float(μ[0]), float(σ[0]), mgx, sgx, mgt, sgt, summary=summary))
+    return out
 
 
 def multistart_base_solve(surrogate, xfinal, *, spatial_lbs, spatial_ubs, guesses, θfixed, device=0):

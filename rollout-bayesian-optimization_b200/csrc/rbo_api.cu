@@ -40,7 +40,7 @@ struct rbo_handle {
   KernelSpec kern;
   int rule_id = 0;
   double sigma_tol = 1e-8, sigma_n2 = 1e-6, k0 = 1, d2k0 = 0, ymin_base = 0;
-  double *Xb = nullptr, *yb = nullptr, *c0 = nullptr, *u0 = nullptr, *Lf = nullptr, *Lb = nullptr, *Lbf = nullptr;
+  double *Xb = nullptr, *yb = nullptr, *c0 = nullptr, *u0 = nullptr, *Lf = nullptr, *Lb = nullptr, *Lbf = nullptr, *x0_batch = nullptr;
   // normals / starts
   int M = 0, hp1 = 0;
   double* rn = nullptr;
@@ -58,7 +58,7 @@ struct rbo_handle {
   size_t cap_ghn = 0, cap_ghw = 0;
   int gh_depth = 0, gh_M = 0;
   size_t dual_cap = 0, forced_cap = 0, tape_cap = 0;
-  size_t cap_Xb = 0, cap_yb = 0, cap_c0 = 0, cap_u0 = 0, cap_Lf = 0, cap_Lb = 0, cap_Lbf = 0, cap_rn = 0, cap_starts = 0;
+  size_t cap_Xb = 0, cap_yb = 0, cap_c0 = 0, cap_u0 = 0, cap_Lf = 0, cap_Lb = 0, cap_Lbf = 0, cap_x0b = 0, cap_rn = 0, cap_starts = 0;
   // last call
   int last_h = 0, last_mode = 0, last_nth = 1;
   bool tape_enabled = true;
@@ -153,7 +153,7 @@ int rbo_destroy(rbo_handle* h) {
   if (!h) return RBO_SUCCESS;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->Xb, h->yb, h->c0, h->u0, h->Lf, h->Lb, h->Lbf, h->rn, h->starts, h->sobol_dirs, h->values, h->grad_x, h->grad_theta, h->xs, h->ys,
+  void* ptrs[] = {h->Xb, h->yb, h->c0, h->u0, h->Lf, h->Lb, h->Lbf, h->x0_batch, h->rn, h->starts, h->sobol_dirs, h->values, h->grad_x, h->grad_theta, h->xs, h->ys,
                   h->gys, h->alphas, h->best_index, h->grad_case, h->status, h->n_evals, h->start_status, h->start_iters, h->work_counter, h->sums,
                   h->dual_dirs, h->x_forced, h->cs_tape, h->gh_nodes, h->gh_weights};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -424,7 +424,7 @@ static double f_eval_exec(double n, double d) { return n * n * (d + 2) + n * (3 
 
 static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, int ntheta, const double* lbs, const double* ubs, int horizon,
                           double fmini, int mode, int flags, const double* dual_dirs_dev, const double* x_forced_dev, bool want_summary,
-                          rbo_summary* summary) {
+                          rbo_summary* summary, const double* x0_batch_dev = nullptr, int B = 1) {
   const bool myopic = (flags & RBO_FLAG_MYOPIC_INTERNAL) != 0, ghq = (flags & RBO_FLAG_GAUSS_HERMITE) != 0;
   if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_rollout: no surrogate (rbo_set_surrogate)");
   if (ghq && !h->gh_nodes) return fail(h, RBO_ERR_STATE, "rbo_rollout: no quadrature data (rbo_set_quadrature)");
@@ -434,7 +434,8 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   if (horizon < 0 || horizon + 1 > RBO_MAXFAN) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_rollout: horizon %d not in [0, %d]", horizon, RBO_MAXFAN - 1);
   if (!myopic && !ghq && horizon + 1 > h->hp1) return fail(h, RBO_ERR_ARG, "rbo_rollout: normals hold %d steps, horizon + 1 = %d needed", h->hp1, horizon + 1);
   if (ghq && horizon + 1 > h->gh_depth) return fail(h, RBO_ERR_ARG, "rbo_rollout: quadrature depth %d < horizon + 1 = %d", h->gh_depth, horizon + 1);
-  const int M = myopic ? 1 : (ghq ? h->gh_M : h->M);
+  const int Ms = myopic ? 1 : (ghq ? h->gh_M : h->M);  // sample indices
+  const int M = Ms * std::max(B, 1);                    // trajectories of this launch
   if ((flags & RBO_FLAG_TEACHER_FORCED) && !x_forced_dev) return fail(h, RBO_ERR_ARG, "rbo_rollout: teacher forcing without x_forced");
   if (mode != RBO_MODE_VALUE && mode != RBO_MODE_VALUE_GRAD) return fail(h, RBO_ERR_ARG, "rbo_rollout: bad mode");
   for (int a = 0; a < h->d; ++a)
@@ -453,7 +454,7 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   P.d = h->d; P.N = h->N; P.N8 = h->N8; P.nb8 = h->nb8; P.nb32 = h->nb32; P.h = horizon; P.S = S; P.W = pc.W; P.RSmax = pc.RSmax; P.NPmax = pc.NPmax; P.xsm = pc.xsm; P.XP = h->N8 + 1;
   P.RSh = pc.RSh;
   P.pl = make_plan(P.d, P.N8, horizon, pc.W, pc.RP, pc.NR, pc.RSmax, pc.NPmax, pc.xsm, pc.RSh);
-  P.CS = h->d + 3; P.RP = pc.RP; P.NR = pc.NR; P.M = M; P.hp1 = h->hp1; P.mode = mode; P.flags = flags; P.ntheta = ntheta;
+  P.CS = h->d + 3; P.RP = pc.RP; P.NR = pc.NR; P.M = M; P.Ms = Ms; P.B = std::max(B, 1); P.x0_batch = (B > 1 || x0_batch_dev) ? x0_batch_dev : nullptr; P.hp1 = h->hp1; P.mode = mode; P.flags = flags; P.ntheta = ntheta;
   P.kern = h->kern; P.rule_id = h->rule_id; P.sigma_tol = h->sigma_tol; P.sigma_n2 = h->sigma_n2; P.k0 = h->k0; P.d2k0 = h->d2k0;
   P.ymin_base = h->ymin_base; P.m52_c = std::sqrt(5.0) / h->kern.th[0]; P.fmini = fmini; P.theta1 = theta[0]; P.htol = h->htol; P.so = h->so;
   for (int a = 0; a < h->d; ++a) { P.x0[a] = x0[a]; P.lbs[a] = lbs[a]; P.ubs[a] = ubs[a]; }
@@ -572,6 +573,33 @@ int rbo_rollout_device(rbo_handle* h, const double* x0, const double* theta, int
                        double fmini, int mode, int flags, const double* dual_dirs_device, const double* x_forced_device, rbo_summary* summary) {
   if (!h) return RBO_ERR_ARG;
   return launch_rollout(h, x0, theta, ntheta, lbs, ubs, horizon, fmini, mode, flags, dual_dirs_device, x_forced_device, summary != nullptr, summary);
+}
+
+int rbo_rollout_batch(rbo_handle* h, const double* x0s, int n_x0, const double* theta, int ntheta, const double* lbs, const double* ubs, int horizon,
+                      double fmini, int mode, const double* dual_dirs, double* values, double* grad_x, double* grad_theta, int32_t* status,
+                      rbo_summary* summary) {
+  if (!h) return RBO_ERR_ARG;
+  if (!x0s || n_x0 < 1 || !values) return fail(h, RBO_ERR_ARG, "rbo_rollout_batch: bad arguments");
+  if (mode == RBO_MODE_VALUE_GRAD && (!grad_x || !grad_theta)) return fail(h, RBO_ERR_ARG, "rbo_rollout_batch: gradient containers missing in VALUE_GRAD mode");
+  if (!h->rn) return fail(h, RBO_ERR_STATE, "rbo_rollout_batch: no normals (rbo_set_normals / rbo_generate_normals)");
+  CK(h, cudaSetDevice(h->device));
+  const size_t Ms = (size_t)h->M, M = Ms * (size_t)n_x0, nd = Ms * std::max(horizon, 0) * h->d;
+  int rc = upload_opt(h, (mode == RBO_MODE_VALUE_GRAD) ? dual_dirs : nullptr, nd, &h->dual_dirs, &h->dual_cap);
+  if (rc) return rc;
+  CK(h, dev_reserve(&h->x0_batch, &h->cap_x0b, (size_t)n_x0 * h->d));
+  CK(h, cudaMemcpyAsync(h->x0_batch, x0s, (size_t)n_x0 * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+  rbo_summary local;
+  rc = launch_rollout(h, x0s, theta, ntheta, lbs, ubs, horizon, fmini, mode, 0, (mode == RBO_MODE_VALUE_GRAD && dual_dirs) ? h->dual_dirs : nullptr, nullptr,
+                      true, summary ? summary : &local, h->x0_batch, n_x0);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(values, h->values, M * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (mode == RBO_MODE_VALUE_GRAD) {
+    CK(h, cudaMemcpyAsync(grad_x, h->grad_x, M * h->d * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(grad_theta, h->grad_theta, M * ntheta * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (status) CK(h, cudaMemcpyAsync(status, h->status, M * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return RBO_SUCCESS;
 }
 
 int rbo_partial_sums_device(rbo_handle* h, double* sums_device, int len) {

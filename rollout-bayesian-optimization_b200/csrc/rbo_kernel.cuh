@@ -26,7 +26,9 @@ struct DevProblem {
   int RSmax, NPmax;       // row splits of the reductions; capacity of the pair list
   int RSh;                // row splits of the Hessian sums (>= RSmax when shared memory allows)
   int xsm, XP;            // base locations staged in shared memory (1) or read through L1 (0); their row pitch
-  int M;                  // trajectories owned by this handle
+  int M;                  // trajectories of this launch (= B * Ms)
+  int Ms, B;              // sample indices owned by this handle; number of starting points evaluated in one launch (trajectory m = b * Ms + sample)
+  const double* x0_batch; // [B][d] starting points when B > 1 (else x0[] below)
   int hp1;                // third dimension of the normals tensor
   int mode, flags, ntheta;
   // model

@@ -496,3 +496,37 @@ def test_full_size_properties(pkg, orc):
     assert np.array_equal(a["grad_case"][pick], ref["grad_case"])
     gscale = np.maximum(np.abs(ref["grad_x"]).max(axis=0, keepdims=True), 1e-6)
     assert np.max(np.abs(a["grad_x"][:, pick] - ref["grad_x"]) / gscale) < 1e-5
+
+
+def test_batch_of_starting_points_equals_serial_calls(pkg, orc):
+    """rbo_rollout_batch (the restarts of the stochastic-ascent outer loop in one launch) is bit-identical to one
+    rbo_rollout call per starting point, and the host mirror returns one ExpectedTrajectoryOutput per column."""
+    wl, sur, rn, starts, dd = setup(pkg, orc, "C2", M=40, N=24, h=2, S=5)
+    rng = np.random.default_rng(3)
+    x0s = np.asfortranarray(wl.lbs[:, None] + (wl.ubs - wl.lbs)[:, None] * rng.random((wl.d, 3)))
+    fmini = float(np.min(sur.y))
+    eng = pkg.RolloutEngine(0)
+    try:
+        eng.set_surrogate(pkg.FantasySurrogate(sur, wl.h))
+        eng.set_normals(rn)
+        eng.set_starts(starts)
+        vb, gxb, gtb = np.zeros((wl.M, 3), order="F"), np.zeros((wl.d, wl.M, 3), order="F"), np.zeros((1, wl.M, 3), order="F")
+        eng.rollout_batch(x0s, wl.theta, wl.lbs, wl.ubs, wl.h, fmini, vb, gxb, gtb, dual_dirs=dd)
+        for b in range(3):
+            v, gx, gt = np.zeros(wl.M), np.zeros((wl.d, wl.M), order="F"), np.zeros((1, wl.M), order="F")
+            eng.rollout(x0s[:, b], wl.theta, wl.lbs, wl.ubs, wl.h, fmini, v, gx, gt, dual_dirs=dd)
+            assert np.array_equal(v, vb[:, b]) and np.array_equal(gx, gxb[:, :, b]) and np.array_equal(gt, gtb[:, :, b])
+    finally:
+        eng.close()
+    fs = pkg.FantasySurrogate(sur, wl.h)
+    T = pkg.Trajectory(sur, fs, start=wl.x0, hypers=wl.theta, horizon=wl.h)
+    tp = pkg.TrajectoryParameters(wl.x0, wl.theta, wl.h, wl.M, False, wl.lbs, wl.ubs, rnstream_sequence=rn)
+    etos = pkg.simulate_trajectory_mc_batch(T, tp, x0s, inner_solve_xstarts=starts, dual_directions=dd)
+    assert len(etos) == 3
+    for b in range(3):
+        assert np.isclose(pkg.mean(etos[b]), vb[:, b].mean(), rtol=1e-13) and np.allclose(pkg.gradient(etos[b]), gxb[:, :, b].mean(axis=1), rtol=1e-12, atol=1e-15)
+    # the oracle at the second starting point
+    wl.x0 = x0s[:, 1].copy()
+    ref = oracle_problem(orc, wl, sur, rn, starts, 1, dual_dirs=dd).rollout()
+    fv, ev = frac_within(vb[:, 1], ref["values"], 1e-8, 1.0)
+    assert fv >= 0.95, ev
