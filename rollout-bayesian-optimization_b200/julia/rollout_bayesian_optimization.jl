@@ -187,6 +187,37 @@ function simulate_trajectory_ghq(T::Trajectory, tp::TrajectoryParameters;
     return ExpectedTrajectoryOutput(μxθ = μxθ, σ_μxθ = σ_μxθ, ∇μx = ∇μx, σ_∇μx = σ_∇μx, ∇μθ = ∇μθ, σ_∇μθ = σ_∇μθ)
 end
 
+# Not in the reference: the estimator at every column of x0s (d x B) in ONE launch -- what a serial loop over
+# simulate_trajectory_mc with set_starting_point!(tp, x0) computes (same normals for every starting point). Returns a vector of
+# ExpectedTrajectoryOutput. Used by drivers that restart the stochastic ascent from a batch of x0 (utils.jl:235-265).
+function simulate_trajectory_mc_batch(T::Trajectory, tp::TrajectoryParameters, x0s::Matrix{Float64}; inner_solve_xstarts::Matrix{Float64})
+    h = _rbo_handle()
+    fs = get_fantasy_surrogate(T)
+    N = get_known_observations(fs)
+    _rbo_set_surrogate!(h, fs.X, fs.L.data, fs.y, fs.cs[1], N, fs.ψ, fs.g, fs.σn2)
+    rn = tp.rnstream_sequence
+    M, d, hor, B = tp.mc_iters, length(tp.x0), tp.horizon, size(x0s, 2)
+    _rbo_check(h, ccall((:rbo_set_normals, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cint, Cint), h.ptr, rn, M, size(rn, 3), 0, M))
+    _rbo_check(h, ccall((:rbo_set_starts, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), h.ptr, inner_solve_xstarts, size(inner_solve_xstarts, 2)))
+    θ = Vector{Float64}(tp.θ)
+    vals = zeros(M, B); gx = zeros(d, M, B); gθ = zeros(length(θ), M, B); status = zeros(Int32, M, B)
+    dual = rand(d, max(hor, 1), M)
+    summary = RboSummary()
+    _rbo_check(h, ccall((:rbo_rollout_batch, librbo), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ref{RboSummary}),
+        h.ptr, x0s, B, θ, length(θ), tp.spatial_lbs, tp.spatial_ubs, hor, minimum(get_observations(get_base_surrogate(T))), 1, dual,
+        vals, gx, gθ, status, summary))
+    bad = findfirst(!=(0), status)
+    isnothing(bad) || error("trajectory $(Tuple(bad)): " * get(_RBO_STATUS, Int(status[bad]), "error"))
+    return map(1:B) do b
+        μ = Distributions.mean(vals[:, b]); ∇μx = vec(Distributions.mean(gx[:, :, b], dims = 2)); ∇μθ = vec(Distributions.mean(gθ[:, :, b], dims = 2))
+        ExpectedTrajectoryOutput(μxθ = μ, σ_μxθ = Distributions.std(vals[:, b], mean = μ), ∇μx = ∇μx,
+                                 σ_∇μx = vec(Distributions.std(gx[:, :, b], dims = 2, mean = ∇μx)), ∇μθ = ∇μθ,
+                                 σ_∇μθ = vec(Distributions.std(gθ[:, :, b], dims = 2, mean = ∇μθ)))
+    end
+end
+
 function multistart_base_solve!(surrogate::Surrogate, xfinal::Vector{T};
         spatial_lbs::Vector{T}, spatial_ubs::Vector{T}, guesses::Matrix{T}, θfixed::Vector{T}) where T <: Real
     if get_name(get_decision_rule(surrogate)) == "Random"                 # rbf_optim.jl:111-114 stays on the host RNG
