@@ -1054,7 +1054,10 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
     __syncthreads();
     const int m = si[I_M];
     if (m >= P.M) break;
-    const int ms = m % P.Ms, mb = m / P.Ms;  // sample index (normals, dual directions, forced locations, nodes) and starting point
+    // sample index (normals, dual directions, forced locations, nodes) and starting point of trajectory m: recomputed at the
+    // few places they are needed instead of being kept live across the whole trajectory
+#define RBO_MS (m % P.Ms)
+#define RBO_MB (m / P.Ms)
 
     // ---- trajectory init: reset!(fs) (rbs.jl:476-480) ----
     for (int i = tid; i < (N8 + RBO_MAXFAN) * 8; i += RBO_THREADS) k.Fp[i] = 0.0;
@@ -1084,9 +1087,9 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
     for (int step = 0; step <= h; ++step) {
       // ============ choose the location x_step ============
       if (step == 0) {
-        if (tid < d) bestx[tid] = P.x0_batch ? __ldg(P.x0_batch + (size_t)mb * d + tid) : P.x0[tid];  // rollout.jl:46
+        if (tid < d) bestx[tid] = P.x0_batch ? __ldg(P.x0_batch + (size_t)RBO_MB * d + tid) : P.x0[tid];  // rollout.jl:46
       } else if (P.flags & RBO_FLAG_TEACHER_FORCED) {
-        if (tid < d) bestx[tid] = P.x_forced[((size_t)ms * h + (step - 1)) * d + tid];
+        if (tid < d) bestx[tid] = P.x_forced[((size_t)RBO_MS * h + (step - 1)) * d + tid];
         if (tid == 0) { si[I_EVALS] = 0; misc[0] = nan(""); }
       } else {
         // multistart_base_solve!(fs, xnext; fantasy_index = step-1) (rollout.jl:58-66, rbf_optim.jl:68-101);
@@ -1148,13 +1151,13 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
             const double* raw = misc + 8 + q1 * q1 + q1;
             const double var = P.k0 - raw[0];  // rbs.jl:528
             if (!(var >= 0.0) && si[I_TSTATUS] == RBO_TRAJ_OK) si[I_TSTATUS] = RBO_TRAJ_NEG_VARIANCE;
-            const double sigma = sqrt(var), node = __ldg(P.gh_nodes + (size_t)ms * P.gh_depth + step), s2n = 1.4142135623730951 * node;
+            const double sigma = sqrt(var), node = __ldg(P.gh_nodes + (size_t)RBO_MS * P.gh_depth + step), s2n = 1.4142135623730951 * node;
             yv = dmu[0] + s2n * sigma;
             for (int a = 0; a < d; ++a) k.gyf[r * d + a] = dmu[1 + a] + s2n * (-raw[1 + a] / sigma);  // rbs.jl:529
           } else {
             bool pd = chol_inplace(Sg, q1, q1);
             if (!pd && si[I_TSTATUS] == RBO_TRAJ_OK) si[I_TSTATUS] = RBO_TRAJ_NOT_PD_JOINT;
-            const double* rnm = P.rn + (size_t)ms + (size_t)P.Ms * q1 * step;
+            const double* rnm = P.rn + (size_t)RBO_MS + (size_t)P.Ms * q1 * step;
             yv = dmu[0] + Sg[0] * __ldg(rnm);
             for (int a = 0; a < d; ++a) {
               double v = dmu[1 + a];
@@ -1210,7 +1213,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
       double val = fmax(P.fmini - best, 0.0);
       if (P.flags & RBO_FLAG_GAUSS_HERMITE) {
         // resolve(gho; fmini) (observables.jl:66-72); get_gradient(gho; at) = weights[at] * gradients[:, at] (observables.jl:157)
-        const double* wq = P.gh_weights + (size_t)ms * P.gh_depth;
+        const double* wq = P.gh_weights + (size_t)RBO_MS * P.gh_depth;
         val = __ldg(wq + t) * val / 1.7724538509055159;
         for (int j = 0; j <= h; ++j)
           for (int a = 0; a < d; ++a) k.gyf[j * d + a] *= __ldg(wq + j);
@@ -1246,7 +1249,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
         __syncthreads();
         if (tid == 0) ybars[t + 1] = 1.0;  // rollout.jl:256
         const int CB_RAW = 0, CB_SOL = d + 3, CB_U = 2 * d + 4, CB_Q = 3 * d + 5;
-        const double* dd_m = P.dual_dirs ? P.dual_dirs + (size_t)ms * h * d : nullptr;
+        const double* dd_m = P.dual_dirs ? P.dual_dirs + (size_t)RBO_MS * h * d : nullptr;
         for (int i = t; i >= 1; --i) {
           // ---- re-evaluate policy solve i: fs(x_i, theta; fantasy_index = i-1) (rollout.jl:114-124) ----
           k.nf = i;
