@@ -383,9 +383,9 @@ static int ensure_outputs(rbo_handle* h, int M, int hor, int S, int d, int nth) 
 
 // Chooses the number of start slots W (starts evaluated in lock-step) so that the shared-memory plan fits.
 struct PlanChoice { int W, RP, NR, RSmax, NPmax, xsm; size_t bytes; int RSh; };
-static bool choose_plan(const rbo_handle* h, int hor, int S, PlanChoice* pc) {
+static bool choose_plan(const rbo_handle* h, int hor, int S, int mode, PlanChoice* pc) {
   const int d = h->d, N8 = h->N8, CS = d + 3, NR = std::max(N8 + RBO_MAXFAN, h->nb32 * RBO_BR);
-  const int nadj = ncols_adjoint(d);
+  const int nadj = (mode == RBO_MODE_VALUE_GRAD) ? ncols_adjoint(d) : 0;  // the adjoint's column plan is only needed with gradients
   // Preference: (i) row splits >= 2 and the base locations in shared memory, with the largest W that still allows it
   // (provided that W covers at least half of the start list); (ii) otherwise the largest W with whatever fits.
   auto try_plan = [&](int W, int RSmax, int xsm) {
@@ -443,7 +443,7 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   CK(h, cudaSetDevice(h->device));
   const int S = std::max(h->S, 1);
   PlanChoice pc;
-  if (!choose_plan(h, horizon, S, &pc))
+  if (!choose_plan(h, horizon, S, mode, &pc))
     return fail(h, RBO_ERR_UNSUPPORTED, "rbo_rollout: problem (d=%d, N=%d, h=%d) needs more than %d bytes of shared memory per CTA", h->d, h->N, horizon, h->max_smem);
   if (getenv("RBO_DEBUG")) fprintf(stderr, "[rbo] plan: W=%d RP=%d NR=%d RSmax=%d NPmax=%d xsm=%d smem=%zu B (limit %d)\n", pc.W, pc.RP, pc.NR, pc.RSmax, pc.NPmax, pc.xsm, pc.bytes, h->max_smem);
   if (getenv("RBO_DEBUG")) fprintf(stderr, "[rbo] plan: RSh=%d\n", pc.RSh);

@@ -530,3 +530,28 @@ def test_batch_of_starting_points_equals_serial_calls(pkg, orc):
     ref = oracle_problem(orc, wl, sur, rn, starts, 1, dual_dirs=dd).rollout()
     fv, ev = frac_within(vb[:, 1], ref["values"], 1e-8, 1.0)
     assert fv >= 0.95, ev
+
+
+def test_value_only_admits_larger_problems(pkg, orc):
+    """Without gradient containers the adjoint's column plan is not reserved, so d = 20 (too wide for value + gradient) fits;
+    asking for gradients at that size fails loudly with RBO_ERR_UNSUPPORTED instead of computing something else."""
+    d, N, h, M, S = 20, 260, 2, 16, 2
+    sur, P, rn, starts, dd, lbs, ubs, x0 = custom_case(pkg, orc, d, N, h, M, S, "Matern52", (0.6 * np.sqrt(d),), "EI", (0.0,))
+    ref = P.rollout()
+    eng = pkg.RolloutEngine(0)
+    try:
+        eng.set_surrogate(pkg.FantasySurrogate(sur, h))
+        eng.set_normals(rn)
+        eng.set_starts(starts)
+        vals, st = np.zeros(M), np.zeros(M, np.int32)
+        eng.rollout(x0, np.zeros(1), lbs, ubs, h, float(np.min(sur.y)), vals, x_forced=np.asfortranarray(ref["xs"][:, 1:, :]), status=st)
+        tape = eng.tape(h)
+        assert np.all(st == 0) and relerr(tape["ys"], ref["ys"]) < 1e-8 and relerr(vals, ref["values"]) < 1e-8
+        free = np.zeros(M)
+        eng.rollout(x0, np.zeros(1), lbs, ubs, h, float(np.min(sur.y)), free)
+        fv, ev = frac_within(free, ref["values"], 1e-7, 1.0)
+        assert fv >= 0.9, ev
+        with pytest.raises(pkg.RboError, match="shared memory"):
+            eng.rollout(x0, np.zeros(1), lbs, ubs, h, float(np.min(sur.y)), vals, np.zeros((d, M), order="F"), np.zeros((1, M), order="F"), dual_dirs=dd)
+    finally:
+        eng.close()
