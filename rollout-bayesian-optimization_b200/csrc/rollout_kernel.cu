@@ -705,6 +705,9 @@ struct K {
       }
 
       AUX_ADD(2, tc0_);
+      // the fantasy-row product below reads ALL top rows of the group's columns: the other warps of the group must have stored
+      // their rows of the last block row first
+      if (FWD && nfan > 0 && wact && NRQ > 1) group_sync(NRQ, gl);
       if (FWD && nfan > 0 && wact && rq == 0) {
         // a = F v_top on the tensor cores (four interleaved accumulator chains), t = b_bot - a, v_bot = Ginv t
         double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
