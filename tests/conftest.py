@@ -16,6 +16,9 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def pkg():
     import __graft_entry__ as g
+    # a clean checkout has no built artefacts (they are git-ignored): build the C-ABI library once (nvcc cross-compiles on CPU)
+    if not os.path.exists(os.path.join(g.PKG_DIR, "csrc", "librbo.so")) and not os.environ.get("RBO_LIB_PATH"):
+        g.build()
     return g.load_package()
 
 
