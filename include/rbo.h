@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RBO_ABI_VERSION 1
+#define RBO_ABI_VERSION 2
 
 typedef struct rbo_handle rbo_handle;
 
@@ -56,18 +56,22 @@ enum {
 };
 
 /* per-start inner-solve status */
-enum { RBO_SOLVE_CONVERGED = 0, RBO_SOLVE_MAXIT = 1, RBO_SOLVE_STEP_TINY = 2, RBO_SOLVE_PRED_TINY = 3, RBO_SOLVE_STALLED = 4, RBO_SOLVE_NAN = 5 };
+enum { RBO_SOLVE_CONVERGED = 0, RBO_SOLVE_MAXIT = 1, RBO_SOLVE_STEP_TINY = 2, RBO_SOLVE_PRED_TINY = 3, RBO_SOLVE_STALLED = 4, RBO_SOLVE_NAN = 5,
+       RBO_SOLVE_FINAL_STEP = 6 /* ended with an interior Newton step below stol, taken without re-evaluation */ };
 
-/* Inner box-constrained maximiser (replaces Optim.IPNewton, rbf_optim.jl:24-30): regularised projected Newton. */
+/* Inner box-constrained maximiser (replaces Optim.IPNewton, rbf_optim.jl:24-30): projected trust-region Newton with the
+ * exact subproblem solution, modelled on the reference's own tr_newton / solve_tr (optim.jl:9-114), on the merit
+ * -log(alpha) (EI, POI) or -alpha (LCB). Radius update and acceptance as optim.jl:93-99. */
 typedef struct {
-  int32_t maxit;    /* accepted steps per start */
-  int32_t maxtry;   /* regularisation retries per step */
-  double gtol;      /* stop: max |projected gradient| <= gtol * max(1, |alpha|) */
-  double xtol;      /* stop: max |step| <= xtol * max(1, max |x|) */
-  double pred_tol;  /* stop: predicted increase <= pred_tol * max(1, |alpha|) */
-  double eta;       /* acceptance ratio */
-  double lam_min;   /* smallest non-zero shift relative to max |diag H| */
-  double lam_up, lam_down;
+  int32_t maxit;     /* accepted steps per start */
+  int32_t maxtry;    /* consecutive rejected / non-descent steps before a start is declared stalled */
+  double gtol;       /* stop: max |projected gradient of alpha| <= gtol * max(1, |alpha|) */
+  double xtol;       /* stop: max |step| <= xtol * max(1, max |x|) */
+  double pred_tol;   /* stop: predicted decrease of the merit <= pred_tol * max(1, |merit|) */
+  double eta;        /* acceptance ratio rho >= eta (optim.jl:99: 0.1) */
+  double delta0_box; /* initial radius = min(delta0_box * widest box side, */
+  double delta0_ell; /*                      delta0_ell * kernel hyper-parameter ktheta[0] (the length-scale)) */
+  double stol;       /* an interior Newton step with max |s| <= stol * max(1, max |x|) is taken without re-evaluation and ends the start */
 } rbo_solver_opts;
 
 /* Summary of one estimator evaluation: ExpectedTrajectoryOutput (trajectory.jl:112-134) computed as

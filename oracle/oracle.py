@@ -20,8 +20,8 @@ FLAG_TEACHER_FORCED, FLAG_FAST_PERTURB, FLAG_FACTORED, FLAG_GAUSS_HERMITE = 1, 2
 
 class SolverOpts(C.Structure):
     _fields_ = [("maxit", C.c_int), ("maxtry", C.c_int), ("gtol", C.c_double), ("xtol", C.c_double),
-                ("pred_tol", C.c_double), ("eta", C.c_double), ("lam_min", C.c_double),
-                ("lam_up", C.c_double), ("lam_down", C.c_double)]
+                ("pred_tol", C.c_double), ("eta", C.c_double), ("delta0_box", C.c_double),
+                ("delta0_ell", C.c_double), ("stol", C.c_double)]
 
 
 _dp = C.POINTER(C.c_double)

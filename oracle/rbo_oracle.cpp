@@ -451,100 +451,256 @@ bool chol_small(double* A, int n) {  // in place lower Cholesky, row-major, retu
   return true;
 }
 
+// ---- exact trust-region subproblem (solve_tr, optim.jl:9-51) without an eigendecomposition ------------------------
+// Householder tridiagonalisation H = Q T Q' (Golub & Van Loan 8.3.1), then every quantity of the secular equation
+// is an O(n) recurrence on T. The CUDA kernel runs the same steps with one warp (lane = row / candidate shift).
+
+// A: n x n symmetric row-major, overwritten: on exit the diagonal a[] / off-diagonal e[] of T are in ta[0..n), te[0..n-1),
+// the Householder vectors v_k (k = 0..n-3) in column k below the sub-diagonal (rows k+1..n-1) and beta[k].
+void householder_tridiag(double* A, int n, double* ta, double* te, double* beta, double* wk /* 2n */) {
+  double* v = wk; double* pw = wk + n;
+  for (int k = 0; k + 2 < n; ++k) {
+    double xn2 = 0;
+    for (int i = k + 1; i < n; ++i) xn2 += A[i * n + k] * A[i * n + k];
+    const double x0 = A[(k + 1) * n + k], alpha = (x0 > 0 ? -1.0 : 1.0) * std::sqrt(xn2);
+    const double vtv = xn2 - 2.0 * alpha * x0 + alpha * alpha;  // |x - alpha e1|^2
+    if (!(vtv > 0) || !(xn2 - x0 * x0 > 0)) { beta[k] = 0; continue; }  // column already reduced
+    const double bk = 2.0 / vtv;
+    for (int i = 0; i < n; ++i) v[i] = (i <= k) ? 0.0 : A[i * n + k];
+    v[k + 1] = x0 - alpha;
+    double pv = 0;
+    for (int i = k + 1; i < n; ++i) { double t = 0; for (int j = k + 1; j < n; ++j) t += A[i * n + j] * v[j]; pw[i] = bk * t; pv += pw[i] * v[i]; }
+    const double kk = 0.5 * bk * pv;
+    for (int i = k + 1; i < n; ++i) pw[i] -= kk * v[i];
+    for (int i = k + 1; i < n; ++i)
+      for (int j = k + 1; j < n; ++j) A[i * n + j] -= v[i] * pw[j] + pw[i] * v[j];
+    A[(k + 1) * n + k] = alpha; A[k * n + (k + 1)] = alpha;
+    for (int i = k + 2; i < n; ++i) { A[i * n + k] = v[i]; A[k * n + i] = 0.0; }
+    // v[k+1] is kept in beta's companion slot
+    beta[k] = bk; beta[n + k] = v[k + 1];
+  }
+  for (int i = 0; i < n; ++i) ta[i] = A[i * n + i];
+  for (int i = 0; i + 1 < n; ++i) te[i] = A[(i + 1) * n + i];
+}
+// y <- H_k y for k ascending (Q' y, transpose = true) or descending (Q y): H_k = I - beta_k v_k v_k'
+void apply_reflectors(const double* A, const double* beta, int n, double* y, bool transpose) {
+  for (int kk = 0; kk + 2 < n; ++kk) {
+    const int k = transpose ? kk : n - 3 - kk;
+    if (beta[k] == 0) continue;
+    double dot = beta[n + k] * y[k + 1];
+    for (int i = k + 2; i < n; ++i) dot += A[i * n + k] * y[i];
+    dot *= beta[k];
+    y[k + 1] -= dot * beta[n + k];
+    for (int i = k + 2; i < n; ++i) y[i] -= dot * A[i * n + k];
+  }
+}
+// Forward recurrences of (T + lam I) = L D L', z = L^-1 b and their lam-derivatives: returns false if a pivot is <= 0 (not
+// positive definite), else |h(lam)|^2 = b'(T + lam I)^-2 b = -d/dlam [sum z_i^2 / d_i].
+bool tri_norm2(const double* ta, const double* te, const double* b, int n, double lam, double* hn2) {
+  double dprev = ta[0] + lam, dd = 1.0, z = b[0], zd = 0.0;
+  if (!(dprev > 0)) return false;
+  double r = 1.0 / dprev;
+  double acc = (z * z * dd) * r * r;  // -(d/dlam)(z^2/d) = (z^2 d' - 2 z z' d) / d^2
+  for (int i = 1; i < n; ++i) {
+    const double e = te[i - 1], er = e * r;
+    const double dn = ta[i] + lam - e * er, ddn = 1.0 + er * er * dd;
+    const double zn = b[i] - er * z, zdn = -er * zd + er * r * dd * z;
+    if (!(dn > 0)) return false;
+    r = 1.0 / dn;
+    acc += (zn * zn * ddn - 2.0 * zn * zdn * dn) * r * r;
+    dprev = dn; dd = ddn; z = zn; zd = zdn;
+  }
+  *hn2 = acc;
+  return true;
+}
+// h = -(T + lam I)^-1 b (requires positive pivots)
+void tri_solve_neg(const double* ta, const double* te, const double* b, int n, double lam, double* h, double* wk /* 2n */) {
+  double* r = wk; double* z = wk + n;
+  r[0] = 1.0 / (ta[0] + lam); z[0] = b[0];
+  for (int i = 1; i < n; ++i) { const double er = te[i - 1] * r[i - 1]; r[i] = 1.0 / (ta[i] + lam - te[i - 1] * er); z[i] = b[i] - er * z[i - 1]; }
+  h[n - 1] = z[n - 1] * r[n - 1];
+  for (int i = n - 2; i >= 0; --i) h[i] = (z[i] - te[i] * h[i + 1]) * r[i];
+  for (int i = 0; i < n; ++i) h[i] = -h[i];
+}
+
+// Exact trust-region step: minimise g'p + p'Hp/2 subject to |p|_2 <= Delta (solve_tr, optim.jl:9-51). The admissible
+// shifts S = {lam >= 0 : T + lam I positive definite and |h(lam)| <= Delta} form a half-line [lam*, inf): lam* = 0 is the
+// interior Newton step (optim.jl:13-21), otherwise the boundary solution, and in the hard case lam* = -lambda_min with
+// |h(lam*)| < Delta, completed along the lowest eigenvector (optim.jl:39-46). lam* is located by TR_ROUNDS rounds of
+// TR_CAND-way multisection (each lane of the CUDA warp tests two candidates), i.e. to 1/(63 * 64^2) = 4e-6 of the initial
+// bracket: a trust-region step does not need |p| = Delta to more than that. Hff: n x n row-major (overwritten).
+// Returns true when the constraint is active ("hit_constraint").
+constexpr int TR_ROUNDS = 3, TR_CAND = 64;
+bool tr_step(double* Hff, const double* gf, int n, double Delta, double* pout, double* work /* >= 8 n */) {
+  double* ta = work; double* te = ta + n; double* beta = te + n; double* gt = beta + 2 * n; double* wk = gt + n;  // wk: 2n
+  if (n == 1) {
+    const double hh = Hff[0], g0 = gf[0];
+    if (hh > 0 && std::fabs(g0 / hh) <= Delta) { pout[0] = -g0 / hh; return false; }
+    pout[0] = (g0 > 0 ? -Delta : Delta);
+    return true;
+  }
+  householder_tridiag(Hff, n, ta, te, beta, wk);
+  double gn2 = 0;
+  for (int i = 0; i < n; ++i) { gt[i] = gf[i]; gn2 += gf[i] * gf[i]; }
+  apply_reflectors(Hff, beta, n, gt, true);
+  double gl = ta[0] - std::fabs(te[0]);  // Gershgorin lower bound of lambda_min(T)
+  for (int i = 1; i < n; ++i) gl = std::min(gl, ta[i] - std::fabs(te[i - 1]) - (i + 1 < n ? std::fabs(te[i]) : 0.0));
+  const double D2 = Delta * Delta;
+  // 0: admissible; 1: positive definite but |h| > Delta; 2: not positive definite
+  auto probe = [&](double lam) { double hn2; if (!tri_norm2(ta, te, gt, n, lam, &hn2)) return 2; return hn2 <= D2 ? 0 : 1; };
+  double lo = 0.0, hi = std::max(0.0, -gl) + std::sqrt(gn2) / Delta;
+  bool hit = true, lo_notpd = false;
+  const int p0 = probe(0.0);
+  if (p0 == 0) { hi = 0.0; hit = false; }
+  else {
+    lo_notpd = p0 == 2;
+    // TR_CAND candidates per round (two per lane of the CUDA warp); the last one is hi, known to be admissible
+    for (int round = 0; round < TR_ROUNDS; ++round) {
+      const double base = lo, wd = hi - lo;
+      int cfirst = TR_CAND - 1;
+      bool below_notpd = lo_notpd;  // state of the candidate just below the first admissible one
+      for (int c = (round == 0 ? 1 : 0); c < TR_CAND - 1; ++c) {
+        const int pr = probe(round == 0 ? wd * (double)c / (TR_CAND - 1) : base + wd * (double)(c + 1) / TR_CAND);
+        if (pr == 0) { cfirst = c; break; }
+        below_notpd = pr == 2;
+      }
+      lo_notpd = below_notpd;
+      if (round == 0) {
+        hi = (cfirst == TR_CAND - 1) ? hi : wd * (double)cfirst / (TR_CAND - 1);
+        lo = wd * (double)(cfirst - 1) / (TR_CAND - 1);
+      } else {
+        hi = (cfirst == TR_CAND - 1) ? hi : base + wd * (double)(cfirst + 1) / TR_CAND;
+        lo = (cfirst == 0) ? base : base + wd * (double)cfirst / TR_CAND;
+      }
+    }
+  }
+  tri_solve_neg(ta, te, gt, n, hi, pout, wk);
+  if (hit && lo_notpd) {
+    double hn2 = 0;
+    for (int i = 0; i < n; ++i) hn2 += pout[i] * pout[i];
+    if (hn2 < D2) {
+      // the admissible set ends where T + lam I stops being positive definite and the step there is still short: hard case
+      // (to the resolution of the search); complete along the lowest eigenvector of T (two steps of inverse iteration at
+      // the barely definite shift) -- this only lowers the model further (optim.jl:39-46)
+      std::vector<double> z(n, 1.0), z2(n);
+      for (int itn = 0; itn < 2; ++itn) {
+        tri_solve_neg(ta, te, z.data(), n, hi, z2.data(), wk);
+        double zn = 0;
+        for (int i = 0; i < n; ++i) zn += z2[i] * z2[i];
+        zn = 1.0 / std::sqrt(zn);
+        for (int i = 0; i < n; ++i) z[i] = z2[i] * zn;
+      }
+      double hz = 0;
+      for (int i = 0; i < n; ++i) hz += pout[i] * z[i];
+      const double tau = -hz + std::sqrt(std::max(hz * hz + (D2 - hn2), 0.0));  // |h + tau z| = Delta, |z| = 1
+      for (int i = 0; i < n; ++i) pout[i] += tau * z[i];
+    }
+  }
+  apply_reflectors(Hff, beta, n, pout, false);
+  return hit;
+}
+
+// One start of the inner solve: trust-region Newton (tr_newton, optim.jl:68-114, with the exact subproblem solver above) on
+// the merit f = -log(alpha) (EI, POI while alpha > 0; the argmax is the same and the tails of EI become near-quadratic) or
+// f = -alpha (LCB), projected onto the box with a gradient-sign active set. Specified in DESIGN.md section 4; the CUDA kernel
+// (slot_logic_warp) implements the same algorithm independently.
 void solve_start(const Ctx& cx, const FS& fs, const double* theta, int fantasy_index, const double* start, StartResult& res) {
   const orc_problem* p = cx.p;
   const orc_solver_opts& o = p->solver;
   const int d = fs.d;
-  std::vector<double> x(d), g(d), H((size_t)d * d), xt(d), sv(d), A((size_t)d * d), pv(d);
+  std::vector<double> x(d), g(d), H((size_t)d * d), xt(d), sv(d), A((size_t)d * d), pv(d), gf(d), work(8 * (size_t)d + 8);
   std::vector<int> fr(d);
-  SX s;
+  SX s, st;
   for (int a = 0; a < d; ++a) x[a] = std::min(std::max(start[a], p->lbs[a]), p->ubs[a]);
   eval_fs(cx, fs, x.data(), theta, fantasy_index, 2, s);
   res.evals = 1; res.iters = 0;
-  double f = -s.g.g;
-  auto load = [&](const SX& sx) {
-    for (int a = 0; a < d; ++a) g[a] = -sx.dal[a];
-    for (int i = 0; i < d * d; ++i) H[i] = -sx.Hal_true[i];
-  };
-  load(s);
-  auto allfinite = [&]() {
-    if (!std::isfinite(f)) return false;
-    for (int a = 0; a < d; ++a) if (!std::isfinite(g[a])) return false;
-    for (int i = 0; i < d * d; ++i) if (!std::isfinite(H[i])) return false;
+  double alpha = s.g.g;
+  const bool logm = p->rule_id != ORC_RULE_LCB && alpha > 0;  // fixed per start
+  auto finite_eval = [&](const SX& sx) {
+    if (!std::isfinite(sx.g.g)) return false;
+    for (int a = 0; a < d; ++a) if (!std::isfinite(sx.dal[a])) return false;
+    for (int i = 0; i < d * d; ++i) if (!std::isfinite(sx.Hal_true[i])) return false;
     return true;
   };
+  double f = 0;
+  auto load = [&](const SX& sx) {
+    alpha = sx.g.g;
+    if (logm) {
+      const double ia = 1.0 / alpha;
+      f = -std::log(alpha);
+      for (int a = 0; a < d; ++a) g[a] = -sx.dal[a] * ia;
+      for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) H[a * d + b] = -sx.Hal_true[a * d + b] * ia + (sx.dal[a] * ia) * (sx.dal[b] * ia);
+    } else {
+      f = -alpha;
+      for (int a = 0; a < d; ++a) g[a] = -sx.dal[a];
+      for (int i = 0; i < d * d; ++i) H[i] = -sx.Hal_true[i];
+    }
+  };
   res.status = ORC_SOLVE_MAXIT;
-  if (!allfinite()) { res.status = ORC_SOLVE_NAN; res.x = x; res.f = std::numeric_limits<double>::quiet_NaN(); return; }
-  double lam = 0;
-  SX st;
-  for (int it = 0; it < o.maxit; ++it) {
+  if (!finite_eval(s)) { res.status = ORC_SOLVE_NAN; res.x = x; res.f = std::numeric_limits<double>::quiet_NaN(); return; }
+  load(s);
+  double wmax = 0, dmax2 = 0;
+  for (int a = 0; a < d; ++a) { const double wd = p->ubs[a] - p->lbs[a]; wmax = std::max(wmax, wd); dmax2 += wd * wd; }
+  const double Dmax = std::sqrt(dmax2);
+  double Delta = std::min(o.delta0_box * wmax, o.delta0_ell * cx.kern.th[0]);
+  int tries = 0;
+  for (;;) {
     int nfree = 0;
-    double pg = 0, hs = 0, mind = std::numeric_limits<double>::infinity();
+    double pg = 0;  // projected gradient of alpha itself (the stopping test does not depend on the merit)
     for (int a = 0; a < d; ++a) {
-      bool act = (x[a] <= p->lbs[a] && g[a] > 0) || (x[a] >= p->ubs[a] && g[a] < 0);
-      if (!act) {
-        fr[nfree++] = a;
-        pg = std::max(pg, std::fabs(g[a]));
-        hs = std::max(hs, std::fabs(H[a * d + a]));
-        mind = std::min(mind, H[a * d + a]);
-      }
+      const bool act = (x[a] <= p->lbs[a] && g[a] > 0) || (x[a] >= p->ubs[a] && g[a] < 0);
+      if (!act) { fr[nfree++] = a; pg = std::max(pg, std::fabs(g[a])); }
     }
-    if (pg <= o.gtol * std::max(1.0, std::fabs(f))) { res.status = ORC_SOLVE_CONVERGED; break; }
-    if (!(hs > 0)) hs = 1;
-    bool accepted = false, done = false;
-    for (int tr = 0; tr < o.maxtry; ++tr) {
-      if (mind + lam <= 0) lam = std::max(lam, -mind + o.lam_min * hs);
-      for (int i = 0; i < nfree; ++i)
-        for (int j = 0; j < nfree; ++j) A[i * nfree + j] = H[fr[i] * d + fr[j]] + (i == j ? lam : 0.0);
-      if (!chol_small(A.data(), nfree)) { lam = std::max(o.lam_up * lam, o.lam_min * hs); continue; }
-      for (int i = 0; i < nfree; ++i) {  // forward
-        double t = -g[fr[i]];
-        for (int k = 0; k < i; ++k) t -= A[i * nfree + k] * pv[k];
-        pv[i] = t / A[i * nfree + i];
-      }
-      for (int i = nfree - 1; i >= 0; --i) {  // backward
-        double t = pv[i];
-        for (int k = i + 1; k < nfree; ++k) t -= A[k * nfree + i] * pv[k];
-        pv[i] = t / A[i * nfree + i];
-      }
-      for (int a = 0; a < d; ++a) xt[a] = x[a];
-      for (int i = 0; i < nfree; ++i) {
-        int a = fr[i];
-        xt[a] = std::min(std::max(x[a] + pv[i], p->lbs[a]), p->ubs[a]);
-      }
-      double smax = 0, xmax = 0;
-      for (int a = 0; a < d; ++a) { sv[a] = xt[a] - x[a]; smax = std::max(smax, std::fabs(sv[a])); xmax = std::max(xmax, std::fabs(x[a])); }
-      if (smax <= o.xtol * std::max(1.0, xmax)) { res.status = ORC_SOLVE_STEP_TINY; done = true; break; }
-      double gs = 0, sHs = 0;
-      for (int a = 0; a < d; ++a) {
-        gs += g[a] * sv[a];
-        double t = 0;
-        for (int b = 0; b < d; ++b) t += H[a * d + b] * sv[b];
-        sHs += sv[a] * t;
-      }
-      double pred = -(gs + 0.5 * sHs);
-      if (!(pred > 0)) { lam = std::max(o.lam_up * lam, o.lam_min * hs); continue; }
-      if (pred <= o.pred_tol * std::max(1.0, std::fabs(f))) { res.status = ORC_SOLVE_PRED_TINY; done = true; break; }
-      eval_fs(cx, fs, xt.data(), theta, fantasy_index, 2, st);
-      res.evals++;
-      double ft = -st.g.g;
-      bool fin = std::isfinite(ft);
-      if (fin) for (int a = 0; a < d; ++a) if (!std::isfinite(st.dal[a])) fin = false;
-      if (fin) for (int i = 0; i < d * d; ++i) if (!std::isfinite(st.Hal_true[i])) fin = false;
-      double ared = f - ft;
-      if (fin && ared >= o.eta * pred) {
-        x = xt; f = ft; load(st);
-        if (ared >= 0.75 * pred) { lam *= o.lam_down; if (lam < o.lam_min * hs) lam = 0; }
-        accepted = true;
-        break;
-      }
-      lam = std::max(o.lam_up * lam, o.lam_min * hs);
+    if (logm) pg *= alpha;
+    if (pg <= o.gtol * std::max(1.0, std::fabs(alpha))) { res.status = ORC_SOLVE_CONVERGED; break; }
+    for (int i = 0; i < nfree; ++i) {
+      gf[i] = g[fr[i]];
+      for (int j = 0; j < nfree; ++j) A[i * nfree + j] = H[fr[i] * d + fr[j]];
     }
-    if (done) break;
-    if (!accepted) { res.status = ORC_SOLVE_STALLED; break; }
-    res.iters = it + 1;
+    const bool hit = tr_step(A.data(), gf.data(), nfree, Delta, pv.data(), work.data());
+    for (int a = 0; a < d; ++a) xt[a] = x[a];
+    for (int i = 0; i < nfree; ++i) { const int a = fr[i]; xt[a] = std::min(std::max(x[a] + pv[i], p->lbs[a]), p->ubs[a]); }
+    double smax = 0, xmax = 0, sn2 = 0;
+    for (int a = 0; a < d; ++a) { sv[a] = xt[a] - x[a]; smax = std::max(smax, std::fabs(sv[a])); xmax = std::max(xmax, std::fabs(x[a])); sn2 += sv[a] * sv[a]; }
+    const double sn = std::sqrt(sn2);
+    if (smax <= o.xtol * std::max(1.0, xmax)) { res.status = ORC_SOLVE_STEP_TINY; break; }
+    double gs = 0, sHs = 0;
+    for (int a = 0; a < d; ++a) {
+      gs += g[a] * sv[a];
+      double t = 0;
+      for (int b = 0; b < d; ++b) t += H[a * d + b] * sv[b];
+      sHs += sv[a] * t;
+    }
+    const double pred = -(gs + 0.5 * sHs);  // mu_diff of optim.jl:88, for the projected step
+    if (!(pred > 0)) {
+      Delta = 0.25 * std::min(Delta, sn);
+      if (++tries >= o.maxtry) { res.status = ORC_SOLVE_STALLED; break; }
+      continue;
+    }
+    const bool pred_tiny = pred <= o.pred_tol * std::max(1.0, std::fabs(f));
+    if (!hit && (pred_tiny || smax <= o.stol * std::max(1.0, xmax))) {
+      // final interior Newton step: taken without another evaluation (its error is O(|s|^2)); alpha follows the model
+      x = xt; alpha = logm ? alpha * std::exp(pred) : alpha + pred; res.status = ORC_SOLVE_FINAL_STEP; break;
+    }
+    if (pred_tiny) { res.status = ORC_SOLVE_PRED_TINY; break; }
+    eval_fs(cx, fs, xt.data(), theta, fantasy_index, 2, st);
+    res.evals++;
+    const bool fin = finite_eval(st) && (!logm || st.g.g > 0);
+    const double ft = fin ? (logm ? -std::log(st.g.g) : -st.g.g) : 0.0;
+    const double rho = fin ? (f - ft) / pred : -1.0;
+    if (fin && rho >= o.eta) {  // optim.jl:99
+      x = xt; load(st);
+      if (rho > 0.75 && hit && sn >= 0.8 * Delta) Delta = std::min(2.0 * Delta, Dmax);  // optim.jl:95-96 (projection may have shortened the step)
+      else if (rho < 0.25) Delta = 0.25 * sn;                                               // optim.jl:93-94
+      tries = 0;
+      if (++res.iters >= o.maxit) { res.status = ORC_SOLVE_MAXIT; break; }
+    } else {
+      Delta = 0.25 * std::min(Delta, sn);
+      if (++tries >= o.maxtry) { res.status = ORC_SOLVE_STALLED; break; }
+    }
   }
-  res.x = x; res.f = f;
+  res.x = x; res.f = -alpha;
 }
 
 int multistart(const Ctx& cx, const FS& fs, const double* theta, int fantasy_index, double* xbest, double* fbest, int* evals,
@@ -829,14 +985,14 @@ extern "C" {
 
 void orc_default_solver_opts(orc_solver_opts* o) {
   o->maxit = 100;
-  o->maxtry = 60;
+  o->maxtry = 30;
   o->gtol = 1e-10;
   o->xtol = 1e-15;
-  o->pred_tol = 1e-17;
-  o->eta = 1e-4;
-  o->lam_min = 1e-8;
-  o->lam_up = 4.0;
-  o->lam_down = 0.25;
+  o->pred_tol = 1e-13;
+  o->eta = 0.1;
+  o->delta0_box = 0.5;
+  o->delta0_ell = 1.0;
+  o->stol = 1e-6;
 }
 
 int orc_rollout(const orc_problem* p, orc_outputs* out) {

@@ -35,17 +35,18 @@ enum {
   ORC_SINGULAR_HESSIAN = 5 /* rollout.jl:188 LU solve hit an exact zero pivot */
 };
 /* per-start solver status */
-enum { ORC_SOLVE_CONVERGED = 0, ORC_SOLVE_MAXIT = 1, ORC_SOLVE_STEP_TINY = 2, ORC_SOLVE_PRED_TINY = 3, ORC_SOLVE_STALLED = 4, ORC_SOLVE_NAN = 5 };
+enum { ORC_SOLVE_CONVERGED = 0, ORC_SOLVE_MAXIT = 1, ORC_SOLVE_STEP_TINY = 2, ORC_SOLVE_PRED_TINY = 3, ORC_SOLVE_STALLED = 4, ORC_SOLVE_NAN = 5, ORC_SOLVE_FINAL_STEP = 6 };
 
 typedef struct {
   int maxit;      /* outer iterations (accepted steps) per start */
-  int maxtry;     /* regularisation retries per outer iteration */
+  int maxtry;     /* consecutive rejected / non-descent trust-region steps before a start is declared stalled */
   double gtol;    /* stop when max |projected gradient| <= gtol * max(1, |alpha|) */
   double xtol;    /* stop when max |step| <= xtol * max(1, max |x|) */
   double pred_tol;/* stop when predicted decrease <= pred_tol * max(1, |alpha|) */
-  double eta;     /* acceptance ratio */
-  double lam_min; /* smallest non-zero shift, relative to max |diag H| */
-  double lam_up, lam_down;
+  double eta;     /* acceptance ratio rho >= eta (optim.jl:99 uses 0.1) */
+  double delta0_box; /* initial trust-region radius: min(delta0_box * widest box side, */
+  double delta0_ell; /*                                  delta0_ell * kernel length-scale theta_k[0]) */
+  double stol;    /* an interior Newton step with max |s| <= stol * max(1, max |x|) is taken without re-evaluation and ends the start */
 } orc_solver_opts;
 
 typedef struct {

@@ -14,8 +14,8 @@ _ip = C.POINTER(C.c_int32)
 
 class SolverOpts(C.Structure):
     _fields_ = [("maxit", C.c_int32), ("maxtry", C.c_int32), ("gtol", C.c_double), ("xtol", C.c_double),
-                ("pred_tol", C.c_double), ("eta", C.c_double), ("lam_min", C.c_double), ("lam_up", C.c_double),
-                ("lam_down", C.c_double)]
+                ("pred_tol", C.c_double), ("eta", C.c_double), ("delta0_box", C.c_double), ("delta0_ell", C.c_double),
+                ("stol", C.c_double)]
 
 
 class Summary(C.Structure):

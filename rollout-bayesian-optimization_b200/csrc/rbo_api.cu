@@ -102,14 +102,14 @@ int rbo_abi_version(void) { return RBO_ABI_VERSION; }
 
 void rbo_default_solver_opts(rbo_solver_opts* o) {
   o->maxit = 100;
-  o->maxtry = 60;
+  o->maxtry = 30;
   o->gtol = 1e-10;
   o->xtol = 1e-15;
-  o->pred_tol = 1e-17;
-  o->eta = 1e-4;
-  o->lam_min = 1e-8;
-  o->lam_up = 4.0;
-  o->lam_down = 0.25;
+  o->pred_tol = 1e-13;
+  o->eta = 0.1;
+  o->delta0_box = 0.5;
+  o->delta0_ell = 1.0;
+  o->stol = 1e-6;
 }
 
 const char* rbo_last_error(const rbo_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -172,7 +172,7 @@ int rbo_set_stream(rbo_handle* h, void* cuda_stream) {
 
 int rbo_set_solver_opts(rbo_handle* h, const rbo_solver_opts* o) {
   if (!h || !o) return RBO_ERR_ARG;
-  if (o->maxit < 1 || o->maxtry < 1 || !(o->lam_up > 1.0) || !(o->lam_down > 0.0 && o->lam_down < 1.0))
+  if (o->maxit < 1 || o->maxtry < 1 || !(o->delta0_box > 0.0) || !(o->delta0_ell > 0.0) || !(o->eta > 0.0 && o->eta < 0.25) || !(o->stol >= 0.0))
     return fail(h, RBO_ERR_ARG, "rbo_set_solver_opts: invalid options");
   h->so = *o;
   return RBO_SUCCESS;

@@ -9,7 +9,7 @@ struct SmemPlan {
   int V, Fp, G, u, Xf, yf, gyf, Xs, stage, mbar;
   int sx, sxt, sg, sH, sA, sp;               // per slot: x, trial x, gradient, Hessian, Cholesky scratch, step
   int sHt, sHref, sga, sdmu, sdsig, sgh;     // per slot: trial Hessian (-H alpha), reference H alpha, grad alpha, grad mu, grad sigma, scalars
-  int sf, slam, spred, shs;                  // per slot scalars
+  int sf, slam, spred, shs, ssn;             // per slot scalars: merit f, trust-region radius, predicted decrease, alpha, |step|_2
   int ppre, ppost, phess;                    // partial sums of the row reductions
   int bestx, misc, adj;                      // [d] best candidate ; scalar/scratch area ; adjoint duals
   int pairs, tbl, ints;                      // int areas (in doubles)
@@ -96,7 +96,7 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.mbar = take(2 * RBO_NSTAGE + 2);
   p.sx = take(W * d); p.sxt = take(W * d); p.sg = take(W * d); p.sH = take(W * dd); p.sA = take(W * dd); p.sp = take(2);
   p.sHt = take(W * dd); p.sHref = take(W * dd); p.sga = take(W * d); p.sdmu = take(W * d); p.sdsig = take(W * d); p.sgh = take(W * 8);
-  p.sf = take(W); p.slam = take(W); p.spred = take(W); p.shs = take(W);
+  p.sf = take(W); p.slam = take(W); p.spred = take(W); p.shs = take(W); p.ssn = take(W);
   p.ppre = take(RSmax * W * q1);
   p.ppost = take(RSmax * NPmax);
   p.phess = take(RSh * W * 2 * (T2 + 1));

@@ -196,7 +196,7 @@ struct K {
   double* cst;     // this CTA's coefficient tape in global memory: cst[k * NR + j] = cs[k][j] (rbs.jl:326)
   unsigned long long* mbar;
   unsigned qglob;  // running count of staged panel chunks (ring position and mbarrier parity)
-  int *alist, *phase, *sstat, *siter, *stry, *sstart, *sevals, *sfr, *colidx, *items, *tbld;
+  int *alist, *phase, *sstat, *siter, *stry, *sstart, *sevals, *sflag, *sfr, *colidx, *items, *tbld;
 
   __device__ K(const DevProblem& P_, double* sm_) : P(P_), pl(P_.pl), sm(sm_) {
     tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
@@ -211,7 +211,7 @@ struct K {
     tbld = reinterpret_cast<int*>(sm + pl.tbl);
     const int W = P.W;
     alist = si + I_ARR; phase = alist + W; sstat = phase + W; siter = sstat + W; stry = siter + W;
-    sstart = stry + W; sevals = sstart + W; sfr = sevals + W; colidx = sfr + 32 * W;
+    sstart = stry + W; sevals = sstart + W; sflag = sevals + W; sfr = sflag + W; colidx = sfr + 32 * W;
   }
 
   __device__ __forceinline__ double xcoord(int j, int p) const {
@@ -811,9 +811,188 @@ struct K {
   }
 
   // ------------------------------------------------------------------------------------------------
-  // One step of the per-start state machine (regularised projected Newton, specified in DESIGN.md section 4),
-  // run by ONE WARP for slot `sl` right after assemble_warp(). Returns true (uniformly) if the slot has a new trial
-  // point in sxt and stays active.
+  // Exact trust-region step by one warp (solve_tr, optim.jl:9-51): minimise g'p + p'Hp/2, |p|_2 <= Delta over the free
+  // coordinates fr[0..n). Lane i < n owns row i / component i of the reduced system and returns p_i. A: n x n scratch.
+  // Householder tridiagonalisation H_FF = Q T Q' (reflectors kept in A below the sub-diagonal), then the admissible shifts
+  // S = {lam >= 0: T + lam I positive definite, |h(lam)| <= Delta} = [lam*, inf) are searched by RBO_TR_ROUNDS rounds of 32-way
+  // multisection -- lane j tests one candidate with the forward LDL' recurrences and their lam-derivatives (no storage) --;
+  // lam* = 0 is the interior Newton step, the hard case is completed along the lowest eigenvector (optim.jl:39-46).
+  // Same algorithm, candidate grid included, as oracle/rbo_oracle.cpp::tr_step.
+  // ------------------------------------------------------------------------------------------------
+  // Two candidate shifts per lane: 0 = admissible, 1 = positive definite but |h(lam)| > Delta, 2 = not positive definite.
+  // yv[i] = component i of Q'g (shared memory). Forward LDL' recurrences of T + lam I and their lam-derivatives:
+  // |h(lam)|^2 = b'(T + lam I)^-2 b = -d/dlam sum z_i^2 / d_i, no storage, no backward pass.
+  __device__ __forceinline__ void tri_probe2(const double* A, const double* yv, int n, double lamA, double lamB, double D2, int& outA, int& outB) const {
+    const double lam[2] = {lamA, lamB};
+    double z[2], r[2], dd[2], zd[2], acc[2];
+    bool ok[2];
+    const double b0 = yv[0], a0 = A[0];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const double dn = a0 + lam[c];
+      ok[c] = dn > 0.0; r[c] = 1.0 / dn; dd[c] = 1.0; zd[c] = 0.0; z[c] = b0; acc[c] = (b0 * b0) * r[c] * r[c];
+    }
+    for (int i = 1; i < n; ++i) {
+      const double e = A[i * n + i - 1], a = A[i * n + i], b = yv[i];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const double er = e * r[c], dn = a + lam[c] - e * er;
+        const double ddn = fma(er * er, dd[c], 1.0), zn = b - er * z[c], zdn = er * (r[c] * dd[c] * z[c] - zd[c]);
+        ok[c] = ok[c] && dn > 0.0;
+        r[c] = 1.0 / dn;
+        acc[c] += (zn * zn * ddn - 2.0 * zn * zdn * dn) * r[c] * r[c];
+        dd[c] = ddn; z[c] = zn; zd[c] = zdn;
+      }
+    }
+    outA = ok[0] ? (acc[0] <= D2 ? 0 : 1) : 2;
+    outB = ok[1] ? (acc[1] <= D2 ? 0 : 1) : 2;
+  }
+  // lane i: component i of -(T + lam I)^-1 b, b[0..n) in shared memory; the pivots must be positive
+  __device__ __forceinline__ double tri_solve_dist(const double* A, const double* b, int n, double lam) const {
+    double myr = 0.0, myz = 0.0, r = 0.0, z = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double bi = b[i];
+      if (i == 0) { r = 1.0 / (A[0] + lam); z = bi; }
+      else { const double e = A[i * n + i - 1], er = e * r; r = 1.0 / (A[i * n + i] + lam - e * er); z = bi - er * z; }
+      if (lane == i) { myr = r; myz = z; }
+    }
+    const double te = (lane + 1 < n) ? A[(lane + 1) * n + lane] : 0.0;
+    double hv = 0.0;
+    for (int i = n - 1; i >= 0; --i) {
+      const double hn = __shfl_sync(FULL, hv, (i + 1) & 31);
+      if (lane == i) hv = (myz - ((i + 1 < n) ? te * hn : 0.0)) * myr;
+    }
+    return -hv;
+  }
+  // A: n x n scratch; yv: n-vector scratch (shared memory, per slot)
+  __device__ bool tr_step_warp(const double* H, const double* g, const int* fr, int n, double Delta, double* A, double* yv, double& pout) {
+    const int d = P.d;
+    const bool in = lane < n;
+    const int myc = in ? fr[lane] : 0;
+    const double gF = in ? g[myc] : 0.0;
+    if (n == 1) {
+      const double hh = H[fr[0] * d + fr[0]], g0 = g[fr[0]];
+      if (hh > 0.0 && fabs(g0 / hh) <= Delta) { pout = -g0 / hh; return false; }
+      pout = g0 > 0.0 ? -Delta : Delta;
+      return true;
+    }
+    for (int e = lane; e < n * n; e += 32) { const int i = e / n, j = e - i * n; A[e] = H[fr[i] * d + fr[j]]; }
+    if (in) yv[lane] = gF;
+    double gn = 0.0;
+    for (int i = 0; i < n; ++i) { const double t = g[fr[i]]; gn = fma(t, t, gn); }
+    gn = sqrt(gn);
+    __syncwarp();
+    // ---- Householder tridiagonalisation H_FF = Q T Q' with y <- Q'y fused in. Every lane evaluates the short dot products
+    // itself from shared memory (cheaper than FP64 shuffle reductions at these sizes). After step k: column k below the
+    // sub-diagonal keeps v_k (rows k+2..), A[k][k+1] its first component and A[k][k+2] beta_k.
+    for (int k = 0; k + 2 < n; ++k) {
+      double xa = 0.0, xb = 0.0;
+      for (int i = k + 1; i + 1 < n; i += 2) { const double u0 = A[i * n + k], u1 = A[(i + 1) * n + k]; xa = fma(u0, u0, xa); xb = fma(u1, u1, xb); }
+      if (((n - k - 1) & 1) != 0) { const double u0 = A[(n - 1) * n + k]; xa = fma(u0, u0, xa); }
+      const double xn2 = xa + xb, x0 = A[(k + 1) * n + k];
+      const double alpha = (x0 > 0.0 ? -1.0 : 1.0) * sqrt(xn2);
+      const double vtv = xn2 - 2.0 * alpha * x0 + alpha * alpha;
+      if (!(vtv > 0.0) || !(xn2 - x0 * x0 > 0.0)) {  // column already reduced (uniform)
+        __syncwarp();
+        if (lane == 0) { A[k * n + k + 2] = 0.0; }
+        __syncwarp();
+        continue;
+      }
+      const double bk = 2.0 / vtv, v1 = x0 - alpha;
+      const bool mine = lane > k && in;
+      const double vi = (lane == k + 1) ? v1 : (mine ? A[lane * n + k] : 0.0);
+      double t = 0.0;
+      if (mine) {
+        t = A[lane * n + k + 1] * v1;
+        for (int j = k + 2; j < n; ++j) t = fma(A[lane * n + j], A[j * n + k], t);
+      }
+      const double pw = bk * t;
+      if (mine) A[k * n + lane] = pw;  // row k beyond the diagonal is free: scratch for p
+      __syncwarp();
+      double pv = A[k * n + k + 1] * v1, vy = v1 * yv[k + 1];
+      for (int j = k + 2; j < n; ++j) { const double vj = A[j * n + k]; pv = fma(A[k * n + j], vj, pv); vy = fma(vj, yv[j], vy); }
+      const double kk = 0.5 * bk * pv, wi = pw - kk * vi;
+      __syncwarp();
+      if (mine) {
+        yv[lane] -= bk * vy * vi;
+        A[lane * n + k + 1] -= vi * (A[k * n + k + 1] - kk * v1) + wi * v1;
+        for (int j = k + 2; j < n; ++j) { const double vj = A[j * n + k]; A[lane * n + j] -= vi * (A[k * n + j] - kk * vj) + wi * vj; }
+      }
+      __syncwarp();
+      if (lane == k + 1) A[lane * n + k] = alpha;                                 // sub-diagonal of T
+      if (lane == k) { A[k * n + k + 1] = v1; A[k * n + k + 2] = bk; }            // first component of v_k, beta_k
+      __syncwarp();
+    }
+    double glo = INFINITY;
+    if (in) glo = A[lane * n + lane] - (lane > 0 ? fabs(A[lane * n + lane - 1]) : 0.0) - (lane + 1 < n ? fabs(A[(lane + 1) * n + lane]) : 0.0);
+    glo = warp_min(glo);  // Gershgorin lower bound of lambda_min(T)
+    const double D2 = Delta * Delta;
+    double lo = 0.0, hi = fmax(0.0, -glo) + gn / Delta;
+    bool hit = true, lo_notpd = false;
+    for (int round = 0; round < RBO_TR_ROUNDS; ++round) {
+      // 64 candidates per round, two per lane (c = lane, lane + 32); the last one is hi, known to be admissible
+      const double base = lo, wd = hi - lo;
+      const double lamA = (round == 0) ? wd * (double)lane / 63.0 : base + wd * (double)(lane + 1) / 64.0;
+      const double lamB = (round == 0) ? wd * (double)(lane + 32) / 63.0 : base + wd * (double)(lane + 33) / 64.0;
+      int oa, ob;
+      tri_probe2(A, yv, n, lamA, lamB, D2, oa, ob);
+      const unsigned long long adm = ((unsigned long long)__ballot_sync(FULL, ob == 0) << 32) | __ballot_sync(FULL, oa == 0) | (1ull << 63);
+      const unsigned long long pdm = ((unsigned long long)__ballot_sync(FULL, ob != 2) << 32) | __ballot_sync(FULL, oa != 2);
+      const int cf = __ffsll((long long)adm) - 1;
+      if (round == 0) {
+        if (cf == 0) { hi = 0.0; hit = false; break; }
+        lo_notpd = ((pdm >> (cf - 1)) & 1ull) == 0ull;
+        hi = (cf == 63) ? hi : wd * (double)cf / 63.0;
+        lo = wd * (double)(cf - 1) / 63.0;
+      } else {
+        if (cf > 0) lo_notpd = ((pdm >> (cf - 1)) & 1ull) == 0ull;
+        hi = (cf == 63) ? hi : base + wd * (double)(cf + 1) / 64.0;
+        lo = (cf == 0) ? base : base + wd * (double)cf / 64.0;
+      }
+    }
+    double h = tri_solve_dist(A, yv, n, hi);
+    if (hit && lo_notpd) {
+      const double hn2 = warp_sum(in ? h * h : 0.0);
+      if (hn2 < D2) {  // hard case (to the resolution of the search): complete along the lowest eigenvector of T
+        __syncwarp();
+        if (in) yv[lane] = 1.0;
+        __syncwarp();
+        double z = 0.0;
+        for (int itn = 0; itn < 2; ++itn) {
+          const double z2 = tri_solve_dist(A, yv, n, hi);
+          const double zn = 1.0 / sqrt(warp_sum(in ? z2 * z2 : 0.0));
+          z = in ? z2 * zn : 0.0;
+          __syncwarp();
+          if (in) yv[lane] = z;
+          __syncwarp();
+        }
+        const double hz = warp_sum(in ? h * z : 0.0);
+        const double tau = -hz + sqrt(fmax(hz * hz + (D2 - hn2), 0.0));
+        h += tau * z;
+      }
+    }
+    // ---- p = Q h: reflectors in descending order
+    __syncwarp();
+    if (in) yv[lane] = h;
+    __syncwarp();
+    for (int k = n - 3; k >= 0; --k) {
+      const double bk = A[k * n + k + 2], v1 = A[k * n + k + 1];
+      if (bk == 0.0) continue;
+      double dot = v1 * yv[k + 1];
+      for (int j = k + 2; j < n; ++j) dot = fma(A[j * n + k], yv[j], dot);
+      const double vi = (lane == k + 1) ? v1 : ((lane > k + 1 && in) ? A[lane * n + k] : 0.0);
+      __syncwarp();
+      if (lane > k && in) yv[lane] -= bk * dot * vi;
+      __syncwarp();
+    }
+    pout = in ? yv[lane] : 0.0;
+    return hit;
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // One step of the per-start state machine (trust-region Newton on the merit -log(alpha) / -alpha, specified in DESIGN.md
+  // section 4; modelled on tr_newton, optim.jl:68-114), run by ONE WARP for slot `sl` right after assemble_warp(). Returns
+  // true (uniformly) if the slot has a new trial point in sxt and stays active.
   // ------------------------------------------------------------------------------------------------
   __device__ bool slot_logic_warp(int sl) {
     const int d = P.d, dd = d * d;
@@ -822,114 +1001,128 @@ struct K {
     double* H = sm + pl.sH + sl * dd; double* A = sm + pl.sA + sl * dd;
     const double* Ht = sm + pl.sHt + sl * dd; const double* ga = sm + pl.sga + sl * d; const double* gh = sm + pl.sgh + sl * 8;
     int* fr = sfr + 32 * sl;
-    double f = (sm + pl.sf)[sl], lam = (sm + pl.slam)[sl], pred = (sm + pl.spred)[sl], hs_st = (sm + pl.shs)[sl];
-    int iters = siter[sl], tries = stry[sl];
-    const double ft = -gh[0];
-    const bool fin = gh[7] != 0.0;
+    // per-slot scalars: merit f, trust-region radius, predicted decrease of the pending trial, alpha at x
+    double f = (sm + pl.sf)[sl], Delta = (sm + pl.slam)[sl], pred = (sm + pl.spred)[sl], alpha = (sm + pl.shs)[sl];
+    int iters = siter[sl], tries = stry[sl], flg = sflag[sl];  // flg bit 0: log merit, bit 1: the pending trial hit the trust-region boundary
+    double sn = (sm + pl.ssn)[sl];
+    const double at = gh[0];
+    bool fin = gh[7] != 0.0;
     const int ph = phase[sl];
     __syncwarp();
     auto store = [&](int status, bool keep) {
       if (lane == 0) {
-        (sm + pl.sf)[sl] = f; (sm + pl.slam)[sl] = lam; (sm + pl.spred)[sl] = pred; (sm + pl.shs)[sl] = hs_st;
-        siter[sl] = iters; stry[sl] = tries; sevals[sl] += 1;
+        (sm + pl.sf)[sl] = f; (sm + pl.slam)[sl] = Delta; (sm + pl.spred)[sl] = pred; (sm + pl.shs)[sl] = alpha; (sm + pl.ssn)[sl] = sn;
+        siter[sl] = iters; stry[sl] = tries; sflag[sl] = flg;
         if (!keep) sstat[sl] = status;
         phase[sl] = keep ? 1 : 2;
       }
       __syncwarp();
       return keep;
     };
-    auto accept_state = [&]() {
-      for (int a = lane; a < d; a += 32) { x[a] = xt[a]; g[a] = -ga[a]; }
-      for (int i = lane; i < dd; i += 32) H[i] = Ht[i];
-      f = ft;
+    auto accept_state = [&]() {  // (x, alpha, f, g, H) <- trial evaluation, in the merit's variables
+      alpha = at;
+      if (flg & 1) {
+        const double ia = 1.0 / at;
+        f = -log(at);
+        for (int a = lane; a < d; a += 32) { x[a] = xt[a]; g[a] = -ga[a] * ia; }
+        for (int i = lane; i < dd; i += 32) { const int a = i / d, b = i - a * d; H[i] = Ht[i] * ia + (ga[a] * ia) * (ga[b] * ia); }
+      } else {
+        f = -at;
+        for (int a = lane; a < d; a += 32) { x[a] = xt[a]; g[a] = -ga[a]; }
+        for (int i = lane; i < dd; i += 32) H[i] = Ht[i];
+      }
       __syncwarp();
     };
+    if (lane == 0) sevals[sl] += 1;
     bool fresh;
     if (ph == 0) {
       if (!fin) {
         for (int a = lane; a < d; a += 32) x[a] = xt[a];
-        f = nan("");
+        alpha = nan("");
         return store(RBO_SOLVE_NAN, false);
       }
+      flg = (P.rule_id != RBO_RULE_LCB && at > 0.0) ? 1 : 0;
       accept_state();
-      lam = 0.0; iters = 0;
+      double wmax = 0.0;
+      for (int a = 0; a < d; ++a) wmax = fmax(wmax, P.ubs[a] - P.lbs[a]);
+      Delta = fmin(o.delta0_box * wmax, o.delta0_ell * P.kern.th[0]);
+      iters = 0; tries = 0;
       fresh = true;
     } else {
-      const double ared = f - ft;
-      if (fin && ared >= o.eta * pred) {
+      fin = fin && (!(flg & 1) || at > 0.0);
+      const double ft = fin ? ((flg & 1) ? -log(at) : -at) : 0.0;
+      const double rho = fin ? (f - ft) / pred : -1.0;
+      if (fin && rho >= o.eta) {  // optim.jl:99
         accept_state();
-        if (ared >= 0.75 * pred) { lam *= o.lam_down; if (lam < o.lam_min * hs_st) lam = 0.0; }
+        if (rho > 0.75 && (flg & 2) && sn >= 0.8 * Delta) {  // optim.jl:95-96
+          double dm2 = 0.0;
+          for (int a = 0; a < d; ++a) { const double wd = P.ubs[a] - P.lbs[a]; dm2 = fma(wd, wd, dm2); }
+          Delta = fmin(2.0 * Delta, sqrt(dm2));
+        } else if (rho < 0.25) Delta = 0.25 * sn;  // optim.jl:93-94
+        tries = 0;
         iters += 1;
         if (iters >= o.maxit) return store(RBO_SOLVE_MAXIT, false);
         fresh = true;
       } else {
-        lam = fmax(o.lam_up * lam, o.lam_min * hs_st);
+        Delta = 0.25 * fmin(Delta, sn);
         tries += 1;
+        if (tries >= o.maxtry) return store(RBO_SOLVE_STALLED, false);
         fresh = false;
       }
     }
-    // active set (lane a <-> coordinate a), projected gradient, Hessian scale
+    // active set (lane a <-> coordinate a) and projected gradient of alpha
     const bool in = lane < d;
-    const double xa = in ? x[lane] : 0.0, gg = in ? g[lane] : 0.0, haa = in ? H[lane * d + lane] : 0.0;
+    const double xa = in ? x[lane] : 0.0, gg = in ? g[lane] : 0.0;
     const bool act = in && ((xa <= P.lbs[lane] && gg > 0.0) || (xa >= P.ubs[lane] && gg < 0.0));
     const unsigned fmask = __ballot_sync(FULL, in && !act);
     const int nfree = __popc(fmask);
     const bool isfree = in && !act;
-    const double pg = warp_max(isfree ? fabs(gg) : 0.0);
-    double hs = warp_max(isfree ? fabs(haa) : 0.0);
-    const double mind = warp_min(isfree ? haa : INFINITY);
-    if (!(hs > 0.0)) hs = 1.0;
-    hs_st = hs;
+    double pg = warp_max(isfree ? fabs(gg) : 0.0);
+    if (flg & 1) pg *= alpha;
     if (lane < nfree) fr[lane] = __fns(fmask, 0, lane + 1);
     __syncwarp();
-    if (fresh) {
-      if (pg <= o.gtol * fmax(1.0, fabs(f))) return store(RBO_SOLVE_CONVERGED, false);
-      tries = 0;
-    }
+    if (fresh && pg <= o.gtol * fmax(1.0, fabs(alpha))) return store(RBO_SOLVE_CONVERGED, false);
     const int myc = lane < nfree ? fr[lane] : 0;  // coordinate owned by this lane in the reduced system
-    while (tries < o.maxtry) {
-      if (mind + lam <= 0.0) lam = fmax(lam, -mind + o.lam_min * hs);
-      for (int e = lane; e < nfree * nfree; e += 32) {
-        int i = e / nfree, j = e - i * nfree;
-        A[e] = H[fr[i] * d + fr[j]] + (i == j ? lam : 0.0);
-      }
-      __syncwarp();
-      if (!chol_warp(A, nfree)) { lam = fmax(o.lam_up * lam, o.lam_min * hs); tries += 1; __syncwarp(); continue; }
-      // solve (H_FF + lam I) p = -g_F : forward then backward substitution, lane i holds component i
-      double t = lane < nfree ? -g[myc] : 0.0;
-      for (int i = 0; i < nfree; ++i) {
-        const double pi = __shfl_sync(FULL, t, i) * A[i * nfree + i];
-        if (lane == i) t = pi;
-        else if (lane > i && lane < nfree) t = fma(-A[lane * nfree + i], pi, t);
-      }
-      for (int i = nfree - 1; i >= 0; --i) {
-        const double pi = __shfl_sync(FULL, t, i) * A[i * nfree + i];
-        if (lane == i) t = pi;
-        else if (lane < i) t = fma(-A[i * nfree + lane], pi, t);
-      }
+    const double xmax = warp_max(fabs(xa));
+    for (;;) {
+      double t;
+      const bool hit = tr_step_warp(H, g, fr, nfree, Delta, A, sm + pl.sdmu + sl * d, t);  // grad mu of the evaluation is not needed any more: scratch
       for (int a = lane; a < d; a += 32) xt[a] = x[a];
       __syncwarp();
       if (lane < nfree) xt[myc] = fmin(fmax(x[myc] + t, P.lbs[myc]), P.ubs[myc]);
       __syncwarp();
       const double sa = in ? xt[lane] - xa : 0.0;
-      const double smax = warp_max(fabs(sa)), xmax = warp_max(fabs(xa));
+      const double smax = warp_max(fabs(sa));
+      sn = sqrt(warp_sum(sa * sa));
       if (smax <= o.xtol * fmax(1.0, xmax)) return store(RBO_SOLVE_STEP_TINY, false);
       double hsv = 0.0;
       if (in) for (int b = 0; b < d; ++b) hsv = fma(H[lane * d + b], xt[b] - x[b], hsv);
       const double gs = warp_sum(gg * sa), sHs = warp_sum(sa * hsv);
-      const double pr = -(gs + 0.5 * sHs);
-      if (!(pr > 0.0)) { lam = fmax(o.lam_up * lam, o.lam_min * hs); tries += 1; continue; }
-      if (pr <= o.pred_tol * fmax(1.0, fabs(f))) return store(RBO_SOLVE_PRED_TINY, false);
+      const double pr = -(gs + 0.5 * sHs);  // mu_diff of optim.jl:88 for the projected step
+      if (!(pr > 0.0)) {
+        Delta = 0.25 * fmin(Delta, sn);
+        tries += 1;
+        if (tries >= o.maxtry) return store(RBO_SOLVE_STALLED, false);
+        continue;
+      }
+      const bool pred_tiny = pr <= o.pred_tol * fmax(1.0, fabs(f));
+      if (!hit && (pred_tiny || smax <= o.stol * fmax(1.0, xmax))) {
+        // final interior Newton step, taken without another evaluation; alpha follows the model
+        for (int a = lane; a < d; a += 32) x[a] = xt[a];
+        alpha = (flg & 1) ? alpha * exp(pr) : alpha + pr;
+        return store(RBO_SOLVE_FINAL_STEP, false);
+      }
+      if (pred_tiny) return store(RBO_SOLVE_PRED_TINY, false);
       pred = pr;
+      flg = (flg & 1) | (hit ? 2 : 0);
       return store(0, true);
     }
-    return store(RBO_SOLVE_STALLED, false);
   }
 
   // loads start `sid` into slot `sl`
   __device__ void load_start(int sl, int sid) {
     const int d = P.d;
-    phase[sl] = 0; sstat[sl] = RBO_SOLVE_MAXIT; siter[sl] = 0; stry[sl] = 0; sevals[sl] = 0; sstart[sl] = sid;
+    phase[sl] = 0; sstat[sl] = RBO_SOLVE_MAXIT; siter[sl] = 0; stry[sl] = 0; sevals[sl] = 0; sstart[sl] = sid; sflag[sl] = 0;
     for (int a = 0; a < d; ++a) {
       double v = __ldg(P.starts + (size_t)sid * d + a);
       (sm + pl.sxt)[sl * d + a] = fmin(fmax(v, P.lbs[a]), P.ubs[a]);
@@ -1006,7 +1199,7 @@ struct K {
           if (phase[sl] == 1) { alist[na2++] = sl; continue; }
           // finished start: candidate (discard NaN, rbf_optim.jl:96), first minimum wins (rbf_optim.jl:97)
           const int sid = sstart[sl];
-          const double f = (sm + pl.sf)[sl];
+          const double f = -(sm + pl.shs)[sl];  // -alpha at the start's final point
           const double* x = sm + pl.sx + sl * d;
           bool bad = !isfinite(f);
           for (int a = 0; a < d; ++a) bad = bad || isnan(x[a]);

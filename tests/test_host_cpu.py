@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(pkg._lib.SYMBOLS), declared ^ set(pkg._lib.SYMBOLS)
-    assert pkg._lib.load().rbo_abi_version() == 1
+    assert pkg._lib.load().rbo_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu(pkg):
