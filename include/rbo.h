@@ -101,6 +101,12 @@ int rbo_set_solver_opts(rbo_handle* h, const rbo_solver_opts* o);
  * det(H alpha) < htol contributes a zero dual (Q3). Exposed so tests can exercise the full adjoint. */
 int rbo_set_htol(rbo_handle* h, double htol);
 
+/* Execution knobs (results do not depend on them beyond rounding): RBO_TUNE_LARGE_N != 0 forces the large-n variant of the
+ * kernel -- work matrix in an L2-resident global scratch instead of shared memory; chosen automatically when a problem does
+ * not fit 227 KB (e.g. n = 1000, d = 20) -- and RBO_TUNE_LARGE_N_SLOTS caps its start slots per round (0 = default). */
+enum { RBO_TUNE_LARGE_N = 1, RBO_TUNE_LARGE_N_SLOTS = 2 };
+int rbo_set_tuning(rbo_handle* h, int key, int value);
+
 /* ---- inputs (resident on the device until replaced) ------------------------------------------ */
 /* The base surrogate the fantasy surrogate is built from: FantasySurrogate(s, h) (rbs.jl:345-381) reads
  * fs.X[:,1:N], fs.L[1:N,1:N], fs.y[1:N], fs.cs[1], fs.sigma_n2, fs.psi, fs.g.

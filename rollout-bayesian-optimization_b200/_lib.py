@@ -34,6 +34,7 @@ SYMBOLS = {
     "rbo_default_solver_opts": (None, [C.POINTER(SolverOpts)]),
     "rbo_set_solver_opts": (C.c_int, [C.c_void_p, C.POINTER(SolverOpts)]),
     "rbo_set_htol": (C.c_int, [C.c_void_p, C.c_double]),
+    "rbo_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "rbo_set_surrogate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _dp, C.c_double, C.c_int,
                                     _dp, C.c_int, C.c_int, C.c_double]),
     "rbo_set_normals": (C.c_int, [C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, C.c_int]),

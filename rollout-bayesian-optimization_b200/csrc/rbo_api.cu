@@ -16,6 +16,7 @@
 
 namespace rbo {
 __global__ void rbo_rollout_kernel(const __grid_constant__ DevProblem P);
+__global__ void rbo_rollout_kernel_largen(const __grid_constant__ DevProblem P);  // same source, work matrix in global memory
 __global__ void rbo_normals_kernel(const unsigned* dirs, double* out, int M_total, int d, int H, int m_begin, int m_count);
 __global__ void rbo_sobol_kernel(const unsigned* dirs, unsigned* out_u32, double* out_f64, int dim, int npoints, const double* lbs, const double* ubs);
 __global__ void rbo_stats_kernel(const double* values, const double* gx, const double* gth, const int* n_evals, const int* best_index, const int* grad_case,
@@ -63,6 +64,10 @@ struct rbo_handle {
   int last_h = 0, last_mode = 0, last_nth = 1;
   bool tape_enabled = true;
   double htol = 1e-4;
+  int vglob_wmax = 0;       // development knob: cap on the start slots of the large-n variant (0 = default)
+  int force_vglob = 0;      // development / test knob: use the large-n variant even when shared memory would do
+  double* Vscratch = nullptr, *Bscratch = nullptr;
+  size_t cap_Vscratch = 0, cap_Bscratch = 0;
 };
 
 static int fail(rbo_handle* h, int code, const char* fmt, ...) {
@@ -125,6 +130,7 @@ int rbo_create(rbo_handle** out, int device_id) {
   rbo_handle* h = new rbo_handle();
   h->device = device_id;
   rbo_default_solver_opts(&h->so);
+  if (const char* e = getenv("RBO_FORCE_LARGE_N")) h->force_vglob = atoi(e) != 0;  // test knob: whole suites under the large-n variant
 #define CKC(call)                                                                                    \
   do {                                                                                               \
     cudaError_t e_ = (call);                                                                         \
@@ -144,6 +150,7 @@ int rbo_create(rbo_handle** out, int device_id) {
   CKC(cudaMalloc((void**)&h->sobol_dirs, sizeof(rbo_sobol_dirs_host)));
   CKC(cudaMemcpy(h->sobol_dirs, rbo_sobol_dirs_host, sizeof(rbo_sobol_dirs_host), cudaMemcpyHostToDevice));
   CKC(cudaFuncSetAttribute(rbo_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+  CKC(cudaFuncSetAttribute(rbo_rollout_kernel_largen, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
 #undef CKC
   *out = h;
   return RBO_SUCCESS;
@@ -155,7 +162,7 @@ int rbo_destroy(rbo_handle* h) {
   cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->Xb, h->yb, h->c0, h->u0, h->Lf, h->Lb, h->Lbf, h->x0_batch, h->rn, h->starts, h->sobol_dirs, h->values, h->grad_x, h->grad_theta, h->xs, h->ys,
                   h->gys, h->alphas, h->best_index, h->grad_case, h->status, h->n_evals, h->start_status, h->start_iters, h->work_counter, h->sums,
-                  h->dual_dirs, h->x_forced, h->cs_tape, h->gh_nodes, h->gh_weights};
+                  h->dual_dirs, h->x_forced, h->cs_tape, h->gh_nodes, h->gh_weights, h->Vscratch, h->Bscratch};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -176,6 +183,16 @@ int rbo_set_solver_opts(rbo_handle* h, const rbo_solver_opts* o) {
     return fail(h, RBO_ERR_ARG, "rbo_set_solver_opts: invalid options");
   h->so = *o;
   return RBO_SUCCESS;
+}
+
+int rbo_set_tuning(rbo_handle* h, int key, int value) {
+  if (!h) return RBO_ERR_ARG;
+  switch (key) {
+    case RBO_TUNE_LARGE_N: h->force_vglob = value != 0; return RBO_SUCCESS;
+    case RBO_TUNE_LARGE_N_SLOTS: if (value < 0 || value > RBO_NCONS) break; h->vglob_wmax = value; return RBO_SUCCESS;
+    default: break;
+  }
+  return fail(h, RBO_ERR_ARG, "rbo_set_tuning: unknown key %d or value %d out of range", key, value);
 }
 
 int rbo_set_htol(rbo_handle* h, double htol) {
@@ -382,38 +399,45 @@ static int ensure_outputs(rbo_handle* h, int M, int hor, int S, int d, int nth) 
 }
 
 // Chooses the number of start slots W (starts evaluated in lock-step) so that the shared-memory plan fits.
-struct PlanChoice { int W, RP, NR, RSmax, NPmax, xsm; size_t bytes; int RSh; };
+struct PlanChoice { int W, RP, NR, RSmax, NPmax, xsm; size_t bytes; int RSh; int vglob; };
 static bool choose_plan(const rbo_handle* h, int hor, int S, int mode, PlanChoice* pc) {
   const int d = h->d, N8 = h->N8, CS = d + 3, NR = std::max(N8 + RBO_MAXFAN, h->nb32 * RBO_BR);
   const int nadj = (mode == RBO_MODE_VALUE_GRAD) ? ncols_adjoint(d) : 0;  // the adjoint's column plan is only needed with gradients
   // Preference: (i) row splits >= 2 and the base locations in shared memory, with the largest W that still allows it
   // (provided that W covers at least half of the start list); (ii) otherwise the largest W with whatever fits.
-  auto try_plan = [&](int W, int RSmax, int xsm) {
+  auto try_plan = [&](int W, int RSmax, int xsm, int vglob = 0) {
     int RP = std::max(W * CS, nadj) + 2;
     if ((RP & 1) == 0) RP += 1;  // odd pitch: conflict-free column walks
     int NPmax = npairs_max(d, W);
-    SmemPlan pl = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm, RSmax);
+    SmemPlan pl = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm, RSmax, vglob);
     size_t bytes = (size_t)pl.total * 8;
     if (bytes > (size_t)h->max_smem) return false;
-    *pc = {W, RP, NR, RSmax, NPmax, xsm, bytes, RSmax};
+    *pc = {W, RP, NR, RSmax, NPmax, xsm, bytes, RSmax, vglob};
     // the Hessian sums are tensor-pipe bound per scheduler: give them enough row splits to occupy every warp if that still fits
     const int want = std::min(4, std::max(RSmax, RBO_NWARPS / W));
     for (int rsh = want; rsh > RSmax; --rsh) {
-      SmemPlan p2 = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm, rsh);
+      SmemPlan p2 = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm, rsh, vglob);
       if ((size_t)p2.total * 8 <= (size_t)h->max_smem) { pc->RSh = rsh; pc->bytes = (size_t)p2.total * 8; break; }
     }
     return true;
   };
   const int Wmax = std::min(S, RBO_NCONS);
-  for (int W = Wmax; W >= std::max(1, std::min(Wmax, (S + 1) / 2)); --W) {
+  for (int W = Wmax; !h->force_vglob && W >= std::max(1, std::min(Wmax, (S + 1) / 2)); --W) {
     int rs = std::min(4, std::max(2, RBO_NWARPS / W));
     if (try_plan(W, rs, 1)) return true;
     if (rs > 2 && try_plan(W, 2, 1)) return true;
   }
-  for (int W = Wmax; W >= 1; --W) {
+  for (int W = Wmax; !h->force_vglob && W >= 1; --W) {
     const int tries[4][2] = {{2, 1}, {1, 1}, {2, 0}, {1, 0}};
     for (auto& t : tries) if (try_plan(W, t[0], t[1])) return true;
   }
+  // Large-n variant (north_star: "L0 ... read through L2 when n is large"; BASELINE config C5): the work matrix moves to a
+  // per-CTA scratch in global memory (it stays L2-resident), everything else keeps its place in shared memory. The base
+  // locations are then read through L1 as well. More start slots per round amortise the stream of L0^-1 over more columns.
+  const int Wg = std::min(Wmax, h->vglob_wmax > 0 ? h->vglob_wmax : 8);
+  for (int W = Wg; W >= 1; --W)
+    for (int rs = std::min(4, std::max(2, RBO_NWARPS / W)); rs >= 1; --rs)
+      if (try_plan(W, rs, 0, 1)) return true;
   return false;
 }
 
@@ -446,14 +470,15 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   if (!choose_plan(h, horizon, S, mode, &pc))
     return fail(h, RBO_ERR_UNSUPPORTED, "rbo_rollout: problem (d=%d, N=%d, h=%d) needs more than %d bytes of shared memory per CTA", h->d, h->N, horizon, h->max_smem);
   if (getenv("RBO_DEBUG")) fprintf(stderr, "[rbo] plan: W=%d RP=%d NR=%d RSmax=%d NPmax=%d xsm=%d smem=%zu B (limit %d)\n", pc.W, pc.RP, pc.NR, pc.RSmax, pc.NPmax, pc.xsm, pc.bytes, h->max_smem);
-  if (getenv("RBO_DEBUG")) fprintf(stderr, "[rbo] plan: RSh=%d\n", pc.RSh);
+  if (getenv("RBO_DEBUG")) fprintf(stderr, "[rbo] plan: RSh=%d vglob=%d\n", pc.RSh, pc.vglob);
   int rc = ensure_outputs(h, M, horizon, S, h->d, ntheta);
   if (rc) return rc;
   DevProblem P;
   memset(&P, 0, sizeof(P));
   P.d = h->d; P.N = h->N; P.N8 = h->N8; P.nb8 = h->nb8; P.nb32 = h->nb32; P.h = horizon; P.S = S; P.W = pc.W; P.RSmax = pc.RSmax; P.NPmax = pc.NPmax; P.xsm = pc.xsm; P.XP = h->N8 + 1;
   P.RSh = pc.RSh;
-  P.pl = make_plan(P.d, P.N8, horizon, pc.W, pc.RP, pc.NR, pc.RSmax, pc.NPmax, pc.xsm, pc.RSh);
+  P.pl = make_plan(P.d, P.N8, horizon, pc.W, pc.RP, pc.NR, pc.RSmax, pc.NPmax, pc.xsm, pc.RSh, pc.vglob);
+  P.vglob = pc.vglob;
   P.CS = h->d + 3; P.RP = pc.RP; P.NR = pc.NR; P.M = M; P.Ms = Ms; P.B = std::max(B, 1); P.x0_batch = (B > 1 || x0_batch_dev) ? x0_batch_dev : nullptr; P.hp1 = h->hp1; P.mode = mode; P.flags = flags; P.ntheta = ntheta;
   P.kern = h->kern; P.rule_id = h->rule_id; P.sigma_tol = h->sigma_tol; P.sigma_n2 = h->sigma_n2; P.k0 = h->k0; P.d2k0 = h->d2k0;
   P.ymin_base = h->ymin_base; P.m52_c = std::sqrt(5.0) / h->kern.th[0]; P.fmini = fmini; P.theta1 = theta[0]; P.htol = h->htol; P.so = h->so;
@@ -470,10 +495,18 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
     size_t need = (size_t)grid * (horizon + 2) * pc.NR;
     if (h->tape_cap < need) { CK(h, dev_realloc(&h->cs_tape, need)); h->tape_cap = need; }
     P.cs_tape = h->cs_tape;
+    if (pc.vglob) {
+      CK(h, dev_reserve(&h->Vscratch, &h->cap_Vscratch, (size_t)grid * pc.NR * pc.RP));
+      P.Vscratch = h->Vscratch;
+      P.bscratch_len = (size_t)h->N8 * 8 * ((std::max(h->d + 1, pc.W) + 7) / 8);  // widest backward pass: q1 columns (adjoint) or W (inner solve)
+      CK(h, dev_reserve(&h->Bscratch, &h->cap_Bscratch, (size_t)grid * P.bscratch_len));
+      P.Bscratch = h->Bscratch;
+    }
   }
   CK(h, cudaMemsetAsync(h->work_counter, 0, 16 * sizeof(int), h->stream));
   CK(h, cudaEventRecord(h->ev0, h->stream));
-  rbo_rollout_kernel<<<grid, RBO_THREADS, pc.bytes, h->stream>>>(P);
+  if (pc.vglob) rbo_rollout_kernel_largen<<<grid, RBO_THREADS, pc.bytes, h->stream>>>(P);
+  else rbo_rollout_kernel<<<grid, RBO_THREADS, pc.bytes, h->stream>>>(P);
   CK(h, cudaGetLastError());
   rbo_stats_kernel<<<1, 1024, 0, h->stream>>>(h->values, mode == RBO_MODE_VALUE_GRAD ? h->grad_x : nullptr, mode == RBO_MODE_VALUE_GRAD ? h->grad_theta : nullptr,
                                               h->n_evals, h->best_index, h->grad_case, h->status, M, h->d, ntheta, horizon, h->sums);

@@ -26,6 +26,10 @@ struct DevProblem {
   int RSmax, NPmax;       // row splits of the reductions; capacity of the pair list
   int RSh;                // row splits of the Hessian sums (>= RSmax when shared memory allows)
   int xsm, XP;            // base locations staged in shared memory (1) or read through L1 (0); their row pitch
+  int vglob;              // 1: the work matrix V does not fit shared memory and lives in Vscratch (large-n variant)
+  double* Vscratch;       // [gridDim.x][NR][RP] when vglob
+  double* Bscratch;       // [gridDim.x][bscratch_len]: out-of-place result of the backward pass (large-n variant)
+  size_t bscratch_len;
   int M;                  // trajectories of this launch (= B * Ms)
   int Ms, B;              // sample indices owned by this handle; number of starting points evaluated in one launch (trajectory m = b * Ms + sample)
   const double* x0_batch; // [B][d] starting points when B > 1 (else x0[] below)
@@ -79,12 +83,12 @@ __host__ __device__ inline int npairs_max(int d, int W) {
   return a > b ? a : b;
 }
 
-__host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int RP, int NR, int RSmax, int NPmax, int xsm, int RSh) {
+__host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int RP, int NR, int RSmax, int NPmax, int xsm, int RSh, int vglob = 0) {
   SmemPlan p;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };  // keep 16-byte alignment
   const int dd = d * d, q1 = d + 1, T2 = d * (d + 1) / 2;
-  p.V = take(NR * RP);
+  p.V = take(vglob ? 0 : NR * RP);  // large-n variant: the work matrix lives in a per-CTA global scratch (L2-resident)
   p.Fp = take((N8 + RBO_MAXFAN) * RBO_PR);
   p.G = take(RBO_MAXFAN * RBO_MAXFAN);
   p.u = take(NR);

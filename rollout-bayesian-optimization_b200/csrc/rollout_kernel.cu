@@ -15,8 +15,23 @@
 //     start queue;
 //   * the adjoint (rollout.jl:233-277) replays the tape: each policy solve i = t..1 is re-evaluated ONCE and its
 //     perturbation columns (rbs.jl:633-764) are pushed into the right-hand sides of the earlier duals.
+//
+// This file is compiled twice (see the Makefile): RBO_VGLOB = 0 is the kernel whose work matrix V lives in shared memory
+// (rbo_rollout_kernel; the compiler then addresses V with shared-memory instructions), RBO_VGLOB = 1 the large-n variant
+// whose V is a per-CTA scratch in global memory that stays L2-resident (rbo_rollout_kernel_largen; north_star: "L0 ... read
+// through L2 when n is large", BASELINE config C5 with n = 1000, d = 20). Everything else is the same code.
 #include "rbo_kernel.cuh"
 
+#ifndef RBO_VGLOB
+#define RBO_VGLOB 0
+#endif
+#if RBO_VGLOB
+#define RBO_KERNEL_NAME rbo_rollout_kernel_largen
+#define g_phase_cycles g_phase_cycles_largen
+#define g_aux_cycles g_aux_cycles_largen
+#else
+#define RBO_KERNEL_NAME rbo_rollout_kernel
+#endif
 
 namespace rbo {
 
@@ -87,7 +102,7 @@ __device__ __forceinline__ void fan_wbot(const double* V, const double* Fp, int 
   // solve has <= 8 columns, far too few to keep a staged panel stream busy, so here the panels of L0^-1 (A-fragment order,
   // Lbf) are read straight from L2, three tiles in flight per warp. Task = (column group, pair of block rows {c, nb-1-c}
   // -- equal work --, row quarter). Results stay in registers until every warp has finished reading the right-hand sides.
-__device__ __noinline__ void bwd_direct(double* V, const double* Fp, const int* colidx, const double* Lbf, int RP, int N8, int nb, int ncols, int nfan, int warp, int lane) {
+__device__ __noinline__ void bwd_direct(double* V, const double* Fp, const int* colidx, const double* Lbf, int RP, int N8, int nb, int ncols, int nfan, int warp, int lane, double* scratch = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int g = lane >> 2, tg = lane & 3;
     const int ngroups = (ncols + 7) >> 3, ncls = (nb + 1) >> 1, tpg = ncls * 4;
@@ -126,6 +141,65 @@ __device__ __noinline__ void bwd_direct(double* V, const double* Fp, const int* 
         if (v0) V[(size_t)(N8 + g) * RP + c0] = w0;
         if (v1) V[(size_t)(N8 + g) * RP + c1] = w1;
       }
+    }
+    if (scratch) {
+      // ---- large-n variant: task = (column group, pair of block rows {c, nb-1-c} -- equal work --); a warp takes all four row
+      // quarters of its block rows, so every right-hand-side fragment read from the (global, L2-resident) work matrix feeds four
+      // tensor-core tiles. The panels stream straight from L2 in A-fragment order. Results go to a per-CTA scratch (out of place:
+      // other tasks still read the right-hand sides) and are copied back, 8 columns per group.
+      const int ntask = ngroups * ncls;
+      __syncthreads();  // fantasy-row update of the top rows stored
+      for (int task = warp; task < ntask; task += RBO_NWARPS) {
+        const int group = task / ncls, cls = task - group * ncls;
+        int cB, c0, c1; bool v0, v1;
+        cols(group, cB, c0, c1, v0, v1);
+        const int rp4 = 4 * RP, rp8 = 8 * RP;
+        for (int hh = 0; hh < 2; ++hh) {
+          const int ib = hh ? nb - 1 - cls : cls, rb = RBO_BR * ib;
+          if (hh && ib == cls) continue;
+          const int nc = nb - ib, chunk0 = nb * ib - ib * (ib - 1) / 2;
+          const int nq = min(4, (N8 - rb + 7) >> 3);  // row quarters of this block row that lie below N8 (uniform)
+          const double2* ap = reinterpret_cast<const double2*>(Lbf) + (size_t)chunk0 * 512 + lane;  // 128 double2 per tile, 4 tiles per chunk
+          const double* vd = V + (size_t)(rb + tg) * RP + cB;
+          double acc[4][4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
+          for (int cc = 0; cc < nc; ++cc) {
+            const double* v = (cc < nc - 1) ? vd + (size_t)(RBO_BR + RBO_CHUNK_K * cc) * RP : vd;
+            double bv[8];
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) { bv[2 * pp] = v[pp * rp8]; bv[2 * pp + 1] = v[pp * rp8 + rp4]; }
+            const double2* ac = ap + (size_t)512 * cc;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q < nq) {
+                double2 A[4];
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) A[pp] = __ldg(ac + 128 * q + 32 * pp);
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                  dmma(acc[q][0], acc[q][1], A[pp].x, bv[2 * pp]);
+                  dmma(acc[q][2], acc[q][3], A[pp].y, bv[2 * pp + 1]);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int row = rb + 8 * q + g;
+            if (q < nq && row < N8) {
+              double* o = scratch + ((size_t)group * N8 + row) * 8 + 2 * tg;
+              o[0] = acc[q][0] + acc[q][2]; o[1] = acc[q][1] + acc[q][3];
+            }
+          }
+        }
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < ngroups * N8 * 8; idx += RBO_THREADS) {
+        const int group = idx / (N8 * 8), r2 = idx - group * N8 * 8, row = r2 >> 3, cc = r2 & 7;
+        if (8 * group + cc < ncols) V[(size_t)row * RP + colidx[8 * group + cc]] = scratch[idx];
+      }
+      return;
     }
     // ---- base rows: w_I = sum_{J >= I} Linv[J][I]^T b_J ; one task per warp and batch, a batch = whole column groups
     const int gpb = RBO_NWARPS / tpg;  // column groups per batch (tpg <= RBO_NWARPS is the caller's condition)
@@ -202,7 +276,12 @@ struct K {
     tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
     nf = 0;
     CCOL = P.RP - 1; UCOL = P.RP - 2;
-    V = sm + pl.V; Fp = sm + pl.Fp; G = sm + pl.G; u = sm + pl.u; Xs = sm + pl.Xs; stage = sm + pl.stage;
+#if RBO_VGLOB
+    V = P.Vscratch + (size_t)blockIdx.x * P.NR * P.RP;
+#else
+    V = sm + pl.V;
+#endif
+    Fp = sm + pl.Fp; G = sm + pl.G; u = sm + pl.u; Xs = sm + pl.Xs; stage = sm + pl.stage;
     mbar = reinterpret_cast<unsigned long long*>(sm + pl.mbar); qglob = 0;
     cst = P.cs_tape + (size_t)blockIdx.x * (P.h + 2) * P.NR;
     Xf = sm + pl.Xf; yf = sm + pl.yf; gyf = sm + pl.gyf; misc = sm + pl.misc; adj = sm + pl.adj; bestx = sm + pl.bestx;
@@ -553,7 +632,13 @@ struct K {
 
   // C-fragment (row g, columns 2 tg, 2 tg + 1) -> B-fragment (k = tg / tg + 4, column g) of the same 8x8 tile.
   __device__ __forceinline__ void c_to_b(double c0, double c1, int g, int tg, double& b0, double& b1) const { rbo::c_to_b(c0, c1, g, tg, b0, b1); }
-  __device__ void bwd_direct(int ncols, int nfan) { rbo::bwd_direct(V, Fp, colidx, P.Lbf, P.RP, P.N8, P.nb32, ncols, nfan, warp, lane); }
+  __device__ void bwd_direct(int ncols, int nfan) {
+#if RBO_VGLOB
+    rbo::bwd_direct(V, Fp, colidx, P.Lbf, P.RP, P.N8, P.nb32, ncols, nfan, warp, lane, P.Bscratch + (size_t)blockIdx.x * P.bscratch_len);
+#else
+    rbo::bwd_direct(V, Fp, colidx, P.Lbf, P.RP, P.N8, P.nb32, ncols, nfan, warp, lane);
+#endif
+  }
 
   // "Triangular solves" of `ncols` columns of V (indices in colidx[]) against L = [L0 0; F G]: FWD: V <- L^-1 V, else V <- L^-T V.
   //  * The host stores the EXPLICIT inverse of L0 as 32-row panels, k-major (pitch RBO_LP), cut into uniform 32-k chunks, so
@@ -569,7 +654,7 @@ struct K {
   __device__ void tri_solve(int ncols, int nfan) {
     if (ncols <= 0) return;
     const int ngroups = (ncols + 7) >> 3;  // a column group = 8 consecutive entries of colidx[]
-    if (!FWD && ((P.nb32 + 1) >> 1) * 4 <= RBO_NWARPS) { bwd_direct(ncols, nfan); return; }
+    if (!FWD && (RBO_VGLOB || ((P.nb32 + 1) >> 1) * 4 <= RBO_NWARPS)) { bwd_direct(ncols, nfan); return; }
     if (ngroups * 4 <= RBO_NCONS) tri_solve_impl<FWD, 4>(ncols, nfan);
     else if (ngroups * 2 <= RBO_NCONS) tri_solve_impl<FWD, 2>(ncols, nfan);
     else tri_solve_impl<FWD, 1>(ncols, nfan);
@@ -1231,7 +1316,7 @@ struct K {
 
 }  // namespace
 
-__global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __grid_constant__ DevProblem P) {
+__global__ void __launch_bounds__(RBO_THREADS, 1) RBO_KERNEL_NAME(const __grid_constant__ DevProblem P) {
   extern __shared__ __align__(128) double smem[];
   K k(P, smem);
   const int tid = k.tid, d = P.d, N8 = P.N8, NR = P.NR, RP = P.RP, h = P.h, q1 = d + 1;
@@ -1634,6 +1719,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) rbo_rollout_kernel(const __gri
   k.pipe_fini();
 }
 
+#if !RBO_VGLOB
 // ----------------------------------------------------------------------------------------------------
 // gen_low_discrepancy_sequence (utils.jl:65-74) on the device: Sobol (utils.jl:4-13, Joe-Kuo direction numbers,
 // Gray-code order, origin skipped) -> Box-Muller with log10 and pair indexing (utils.jl:23-43, Q8) -> the
@@ -1760,10 +1846,16 @@ __global__ void rbo_fp64_peak_kernel(double* out, int iters) {
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+#endif  // !RBO_VGLOB
+
 }  // namespace rbo
 
 #ifdef RBO_PHASE_TIMERS
 // development aid (not part of include/rbo.h): per-phase cycle counters of the rollout kernel
+#if RBO_VGLOB
+#define rbo_debug_phase_cycles rbo_debug_phase_cycles_largen
+#define rbo_debug_aux_cycles rbo_debug_aux_cycles_largen
+#endif
 extern "C" int rbo_debug_phase_cycles(void*, unsigned long long* out16, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out16, rbo::g_phase_cycles, sizeof(unsigned long long) * 16);

@@ -9,23 +9,26 @@ import __graft_entry__ as g
 NAMES = ["fill_columns", "reduce_pre", "fwd_solve", "reduce_post", "bwd_solve", "reduce_hess", "slot_logic", "bookkeeping",
          "  logic:assemble(w0)", "round_gap", "draw+condition", "adjoint", "wait_full(fwd,w0)", "wait_full(bwd,w0)", "  logic:solver(w0)", "rounds"]
 
-def main(name="C3", M=296):
+def main(name="C3", M=296, large_n=False):
     pkg = g.load_package()
     wl = pkg.problems.make_workload(name, M=M)
     sur = wl.surrogate()
     eng = pkg.RolloutEngine(0)
+    if large_n:
+        eng.set_tuning(large_n=True)
     eng.set_surrogate(pkg.FantasySurrogate(sur, wl.h))
     eng.generate_normals(M, wl.h + 1)
     eng.set_starts(pkg.generate_initial_guesses(wl.S, wl.lbs, wl.ubs))
     dd = np.asfortranarray(np.random.default_rng(7).random((wl.d, wl.h, M)))
     vals, gx, gt = np.zeros(M), np.zeros((wl.d, M), order="F"), np.zeros((1, M), order="F")
     out = (ctypes.c_ulonglong * 16)()
-    fn = eng.lib.rbo_debug_phase_cycles
+    sfx = "_largen" if (large_n or name == "C5") else ""
+    fn = getattr(eng.lib, "rbo_debug_phase_cycles" + sfx)
     fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
     s = eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), vals, gx, gt, dual_dirs=dd)
     fn(eng.handle.h, out, 1)
     aux = (ctypes.c_ulonglong * 16)()
-    fa = eng.lib.rbo_debug_aux_cycles
+    fa = getattr(eng.lib, "rbo_debug_aux_cycles" + sfx)
     fa.argtypes = fn.argtypes
     fa(eng.handle.h, aux, 1)
     s = eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), vals, gx, gt, dual_dirs=dd)
@@ -45,4 +48,4 @@ def main(name="C3", M=296):
     eng.close()
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "C3", int(sys.argv[2]) if len(sys.argv) > 2 else 296)
+    main(sys.argv[1] if len(sys.argv) > 1 else "C3", int(sys.argv[2]) if len(sys.argv) > 2 else 296, len(sys.argv) > 3 and sys.argv[3] == "--large-n")
