@@ -35,6 +35,8 @@ import __graft_entry__ as graft  # noqa: E402
 
 METRIC = "rollout trajectories/sec (value+grad)"
 UNIT = "trajectories/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the rollout kernel (ncu --set full, 1 GPU, default M): (bytes, capture)
+TRAFFIC_NCU = {"C3": (15742464, "profiles/r1f_dram_fullM.csv")}
 
 
 def parse():
@@ -49,11 +51,13 @@ def parse():
                     help="reference = gen_low_discrepancy_sequence (utils.jl:65-74) on the device; iid = seeded N(0,1)")
     ap.add_argument("--cpu-sample", type=int, default=None, help="trajectories in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sga-iters", type=int, default=100, help="C4: Adam iterations of the full stochastic-gradient-ascent loop")
     return ap.parse_args()
 
 
 def workload_config(wl, normals, n_gpus):
-    return {"workload": f"{wl.name}: d={wl.d} n={wl.N} h={wl.h} M={wl.M} starts={wl.S}+2 Matern52(l={wl.ell}) EI value+adjoint-gradient FP64",
+    return {"workload": f"{wl.name}: d={wl.d} n={wl.N} h={wl.h} M={wl.M} starts={wl.S}+2 Matern52(l={wl.ell}) EI {'value+adjoint-gradient' if wl.with_grad else 'value only'} FP64"
+                        + (" -- a step is ONE Adam iteration of the stochastic-gradient-ascent loop (utils.jl:235-265), inputs resident" if wl.name == "C4" else ""),
             "normals": "gen_low_discrepancy_sequence (Sobol + log10 Box-Muller, generated on device)" if normals == "reference" else "iid N(0,1), numpy seed 1906",
             "sharding": f"samples split contiguously over {n_gpus} GPU(s); one all-reduce of 1+3(1+d+ntheta) doubles per step",
             "l2": "L2 flushed between timed steps (256 MiB write)"}
@@ -104,21 +108,37 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_oracle_problem(orc, wl, sur, rn, starts, dd, nthreads=0):
-    return graft._oracle_problem(orc, wl, sur, rn, starts, 1, dual_dirs=dd, nthreads=nthreads)
+def build_oracle_problem(orc, wl, sur, rn, starts, dd, nthreads=0, mode=1):
+    return graft._oracle_problem(orc, wl, sur, rn, starts, mode, dual_dirs=dd, nthreads=nthreads)
 
 
-def cpu_baseline(wl_name, sample, nthreads, normals):
-    """The oracle (CPU restatement of the reference) on `sample` trajectories of the workload, all host threads."""
+# trajectories per host core in the CPU sample: about 5-15 s of oracle time on the GPU box's cores
+CPU_SAMPLE_PER_CORE = {"C1": 512, "C2": 96, "C3": 48, "C4": 16, "C5": 2}
+
+
+def workload_inputs(pkg, orc_or_none, wl, normals, M):
+    """Full-M normals / dual directions of the workload on the host (the CPU legs slice their sample from these)."""
+    if normals == "reference":
+        from oracle import oracle as orc
+        rn = orc.gen_low_discrepancy_sequence(M, wl.d, wl.h + 1)
+    else:
+        rn = np.asfortranarray(np.random.default_rng(1906).standard_normal((M, wl.d + 1, wl.h + 1)))
+    dd = np.asfortranarray(np.random.default_rng(7).random((wl.d, max(wl.h, 1), M)))
+    return rn, dd
+
+
+def cpu_leg(wl_name, M, sample, nthreads, normals, rn_full=None, dd_full=None):
+    """The oracle (CPU restatement of the reference) on the FIRST `sample` sample indices of the workload's own M-trajectory
+    normals tensor (so its per-trajectory results are comparable with the GPU arm's), `nthreads` host threads."""
     from oracle import oracle as orc
     pkg = graft.load_package()
-    wl = pkg.problems.make_workload(wl_name, M=sample)
+    wl = pkg.problems.make_workload(wl_name, M=M)
     sur = wl.surrogate()
-    rn = orc.gen_low_discrepancy_sequence(sample, wl.d, wl.h + 1) if normals == "reference" else \
-        np.asfortranarray(np.random.default_rng(1906).standard_normal((sample, wl.d + 1, wl.h + 1)))
+    if rn_full is None:
+        rn_full, dd_full = workload_inputs(pkg, orc, wl, normals, M)
+    rn = np.asfortranarray(rn_full[:sample]); dd = np.asfortranarray(dd_full[:, :, :sample])
     starts = orc.generate_initial_guesses(wl.S, wl.lbs, wl.ubs)
-    dd = np.asfortranarray(np.random.default_rng(7).random((wl.d, wl.h, sample)))
-    P = build_oracle_problem(orc, wl, sur, rn, starts, dd, nthreads)
+    P = build_oracle_problem(orc, wl, sur, rn, starts, dd, nthreads, mode=1 if wl.with_grad else 0)
     t0 = time.perf_counter()
     r = P.rollout(tape=False)
     dt = time.perf_counter() - t0
@@ -134,19 +154,23 @@ def run_reference(args):
     pkg = graft.load_package()
     wl_full = pkg.problems.make_workload(args.workload, M=args.M)
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or max(cores * 48, 256)
+    sample = min(wl_full.M, args.cpu_sample or max(cores * CPU_SAMPLE_PER_CORE.get(args.workload, 16), 16))
+    rn_full, dd_full = workload_inputs(pkg, None, wl_full, args.normals, wl_full.M)
     times = []
     for i in range(args.warmup + args.steps):
-        tput, dt, _ = cpu_baseline(args.workload, sample, cores, args.normals)
+        tput, dt, _ = cpu_leg(args.workload, wl_full.M, sample, cores, args.normals, rn_full, dd_full)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms * 1e-3)
+    s1 = max(2, min(sample, sample // cores))
+    t1, dt1, _ = cpu_leg(args.workload, wl_full.M, s1, 1, args.normals, rn_full, dd_full)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(wl_full, args.normals, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} of {wl_full.M} trajectories per step (oracle/rbo_oracle.cpp, OpenMP dynamic schedule; Julia reference not runnable here)"},
+                             "sample": f"first {sample} of {wl_full.M} sample indices per step (oracle/rbo_oracle.cpp, OpenMP dynamic schedule; Julia reference not runnable here)",
+                             "single_thread": {"value": t1, "unit": UNIT, "sample": f"first {s1} sample indices, 1 thread (the reference itself is serial, rollout.jl:293)"}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -173,6 +197,9 @@ def main():
 
     wl = pkg.problems.make_workload(args.workload, M=args.M)
     M, d, h = wl.M, wl.d, wl.h
+    want_grad = bool(wl.with_grad)
+    mode = 1 if want_grad else 0
+    sga = args.workload == "C4"  # BASELINE config 4: the stochastic-gradient-ascent loop; a step = one optimizer iteration
     m_begin = (M * rank) // world
     m_count = (M * (rank + 1)) // world - m_begin
     sur = wl.surrogate()
@@ -183,7 +210,7 @@ def main():
     eng = pkg.RolloutEngine(dev.index, stream=stream.cuda_stream)
     starts = pkg.generate_initial_guesses(wl.S, wl.lbs, wl.ubs, device=dev.index)
     rng = np.random.default_rng(7)
-    dd_full = np.asfortranarray(rng.random((d, h, M)))
+    dd_full = np.asfortranarray(rng.random((d, max(h, 1), M)))
     dd_host = np.ascontiguousarray(dd_full[:, :, m_begin:m_begin + m_count].transpose(2, 1, 0))  # [m][h][d] == column-major d x h x m
     dd_dev = torch.from_numpy(dd_host).to(dev)
 
@@ -199,18 +226,37 @@ def main():
 
     nsum = 1 + 3 * (1 + d + 1)
     sums = torch.zeros(nsum, dtype=torch.float64, device=dev)
+    sums_pin = torch.empty(nsum, dtype=torch.float64, pin_memory=True)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    p = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    x_cur = wl.x0.copy()
+    adam = pkg.Adam()  # optimizers.jl:35-40 defaults: eta 1e-3, beta1 .9, beta2 .999, eps 1e-8
+
+    def finalize(fin):
+        mean_v, std_v = ctypes.c_double(), ctypes.c_double()
+        gm, gs, tm, ts = np.zeros(d), np.zeros(d), np.zeros(1), np.zeros(1)
+        eng.lib.rbo_finalize_sums(p(fin), d, 1, ctypes.byref(mean_v), ctypes.byref(std_v), p(gm), p(gs), p(tm), p(ts))
+        return mean_v.value, std_v.value, gm, gs
+
     def device_step():
-        eng.rollout_device(wl.x0, wl.theta, wl.lbs, wl.ubs, h, fmini, 1, dual_dirs_ptr=dd_dev.data_ptr())
+        eng.rollout_device(x_cur, wl.theta, wl.lbs, wl.ubs, h, fmini, mode, dual_dirs_ptr=dd_dev.data_ptr() if want_grad else None)
         eng.handle.check(eng.lib.rbo_partial_sums_device(eng.handle.h, ctypes.c_void_p(sums.data_ptr()), nsum))
         if world > 1:
             dist.all_reduce(sums)
+        if sga:
+            # stochastic_solve (utils.jl:235-265): the ascent step needs the gradient estimate on the host -- 37 doubles D2H,
+            # then update!(optimizer; x, grad) (optimizers.jl:48-75); inputs stay resident, only x0 changes (common random numbers)
+            sums_pin.copy_(sums, non_blocking=True)
+            stream.synchronize()
+            _, _, gm, _ = finalize(sums_pin.numpy())
+            pkg.update_optimizer(adam, x_cur, gm)
+            np.clip(x_cur, wl.lbs, wl.ubs, out=x_cur)
 
     def timed(step_fn, steps, warmup):
         for _ in range(warmup):
@@ -237,13 +283,32 @@ def main():
     ms_per_step = total_ms / args.steps
     value = M / (ms_per_step * 1e-3)
 
-    # statistics of the last step (checks the all-reduce path) and accounting from one summarised launch
-    fin = sums.cpu().numpy()
-    mean_v, std_v = ctypes.c_double(), ctypes.c_double()
-    gm, gs, tm, ts = np.zeros(d), np.zeros(d), np.zeros(1), np.zeros(1)
-    p = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-    eng.lib.rbo_finalize_sums(p(fin), d, 1, ctypes.byref(mean_v), ctypes.byref(std_v), p(gm), p(gs), p(tm), p(ts))
-    summ = eng.rollout_device(wl.x0, wl.theta, wl.lbs, wl.ubs, h, fmini, 1, dual_dirs_ptr=dd_dev.data_ptr(), want_summary=True)
+    sga_info = None
+    if sga:
+        # the whole loop of BASELINE config 4: args.sga_iters Adam iterations from the box centre, ESWAVS stop disabled
+        x_cur[:] = wl.x0
+        adam = pkg.Adam()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.sga_iters):
+            device_step()
+        e1.record(stream)
+        barrier()
+        tl = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        sga_info = {"iterations": args.sga_iters, "total_ms": float(tl.item()), "ms_per_iteration": float(tl.item()) / args.sga_iters,
+                    "x_final": x_cur.tolist(), "optimizer": "Adam(eta=1e-3, beta1=0.9, beta2=0.999, eps=1e-8), ESWAVS off (utils.jl:235-265, optimizers.jl:35-75)"}
+        x_cur[:] = wl.x0
+
+    # statistics of one more step at the workload's x0 (checks the all-reduce path) and accounting from one summarised launch
+    sga_saved, sga = sga, False
+    device_step()
+    sga = sga_saved
+    stream.synchronize()
+    mean_v, std_v, gm, gs = finalize(sums.cpu().numpy())
+    summ = eng.rollout_device(wl.x0, wl.theta, wl.lbs, wl.ubs, h, fmini, mode, dual_dirs_ptr=dd_dev.data_ptr() if want_grad else None, want_summary=True)
     acct = torch.tensor([summ.flops, summ.flops_executed, float(summ.n_evals), float(summ.n_failed), summ.kernel_ms], dtype=torch.float64, device=dev)
     kmax = torch.tensor([summ.kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -258,21 +323,20 @@ def main():
         return t.numpy().reshape(shape, order=order), t
 
     rn_pin, _k1 = pinned(rn_shard.shape); rn_pin[...] = rn_shard
-    dd_pin, _k2 = pinned((d, h, m_count)); dd_pin[...] = dd_full[:, :, m_begin:m_begin + m_count]
+    dd_pin, _k2 = pinned((d, max(h, 1), m_count)); dd_pin[...] = dd_full[:, :, m_begin:m_begin + m_count]
     res_pin, _k3 = pinned((m_count,)); gx_pin, _k4 = pinned((d, m_count)); gt_pin, _k5 = pinned((1, m_count))
     st_pin, _k6 = pinned((m_count,), np.int32)
     starts_pin, _k7 = pinned(starts.shape); starts_pin[...] = starts
     N = sur.observed
-    N8 = (N + 7) // 8 * 8
-    nb8 = N8 // 8
-    h2d = 8 * (d * N8 + N + 2 * N8 + 32 * nb8 * (nb8 + 1) + 8 * N8 * nb8 - 32 * nb8 * (nb8 - 1)) + rn_pin.nbytes + starts_pin.nbytes + dd_pin.nbytes
-    d2h = res_pin.nbytes + gx_pin.nbytes + gt_pin.nbytes + st_pin.nbytes + (nsum + 32) * 8
+    h2d = 8 * (d * N + N * N + 2 * N) + rn_pin.nbytes + starts_pin.nbytes + (dd_pin.nbytes if want_grad else 0)  # X, L, y, c as the caller holds them + normals, starts, dual directions
+    d2h = res_pin.nbytes + ((gx_pin.nbytes + gt_pin.nbytes) if want_grad else 0) + st_pin.nbytes + (nsum + 32) * 8
 
     def e2e_step():
-        eng.set_surrogate(fs)                       # fs.X, fs.L, fs.y, fs.cs[1] -> device (packed on the way)
+        eng.set_surrogate(fs)                       # fs.X, fs.L, fs.y, fs.cs[1] -> device (inverted and packed on the device)
         eng.set_normals(rn_pin)                     # tp.rnstream_sequence shard
         eng.set_starts(starts_pin)                  # inner_solve_xstarts
-        eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, h, fmini, res_pin, gx_pin, gt_pin, dual_dirs=dd_pin, status=st_pin)
+        eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, h, fmini, res_pin, gx_pin if want_grad else None, gt_pin if want_grad else None,
+                    dual_dirs=dd_pin if want_grad else None, status=st_pin)
         if world > 1:
             eng.handle.check(eng.lib.rbo_partial_sums_device(eng.handle.h, ctypes.c_void_p(sums.data_ptr()), nsum))
             dist.all_reduce(sums)
@@ -288,48 +352,70 @@ def main():
     _t("set_surrogate", lambda: eng.set_surrogate(fs))
     _t("set_normals", lambda: eng.set_normals(rn_pin))
     _t("set_starts", lambda: eng.set_starts(starts_pin))
-    _t("rollout+d2h", lambda: eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, h, fmini, res_pin, gx_pin, gt_pin, dual_dirs=dd_pin, status=st_pin))
-
-    if rank == 0:
-        peak_tf = eng.fp64_peak()
-        kernel_ms = float(kmax.item())
-        achieved_tf = acct[0] / (kernel_ms * 1e-3) / 1e12 / 1.0  # whole-job flops / slowest rank's kernel time
-        achieved_per_gpu = achieved_tf / world
-        cpu = None
-        if not args.no_cpu_baseline and world >= 1:
-            cores = os.cpu_count() or 1
-            sample = args.cpu_sample or max(cores * 48, 256)
-            tput, dt, r = cpu_baseline(args.workload, sample, cores, args.normals)
-            cpu = {"value": tput, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{sample} of {M} trajectories in {dt:.1f} s (oracle/rbo_oracle.cpp = C++/OpenMP restatement of the reference; Julia not installed)"}
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(wl, args.normals, world),
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
-                    "steps": e2e_steps, "all_trajectories_ok": ok_e2e, "host_breakdown_ms": brk},
-            "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "tensor", "pipe": "FP64 (mma.sync.m8n8k4.f64 and DFMA share the same 64 FMA/clk/SM)", "achieved": achieved_per_gpu, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_per_gpu / peak_tf,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on the default workload
-                         # (C3, M = 16384, 1 GPU), from the ncu capture in profiles/r1f_dram_fullM.csv: 15 340 032 + 402 432 B --
-                         # i.e. the normals, dual directions and outputs once; the rest stays in L2 / shared memory
-                         "traffic": 15742464 if (args.workload == "C3" and args.M is None and world == 1) else None,
-                         "traffic_unit": "bytes per launch (ncu, profiles/r1f_dram_fullM.csv)",
-                         "kernel": "rbo_rollout_kernel", "kernel_ms": kernel_ms,
-                         "flops_per_launch": acct[0] / world, "flops_executed_per_launch": acct[1] / world,
-                         "frac_executed": acct[1] / world / (kernel_ms * 1e-3) / 1e12 / peak_tf,
-                         "peak_source": "rbo_fp64_peak: dense FP64 FMA micro-benchmark in this process (MEASURED_PEAKS.json has no FP64 figure)",
-                         "kernel_share_of_step": kernel_ms / ms_per_step},
-            "cpu_baseline": cpu,
-            "estimate": {"mean": mean_v.value, "std": std_v.value, "grad_x_mean": gm.tolist(), "n_failed": int(acct[3]),
-                         "acquisition_evals_per_trajectory": acct[2] / M},
-        }
-        print(json.dumps(line), flush=True)
+    _t("rollout+d2h", lambda: eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, h, fmini, res_pin, gx_pin if want_grad else None, gt_pin if want_grad else None,
+                                          dual_dirs=dd_pin if want_grad else None, status=st_pin))
+    peak_tf = eng.fp64_peak() if rank == 0 else 0.0
+    gpu_vals, gpu_gx = res_pin.copy(), gx_pin.copy()
     eng.close()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        dist.destroy_process_group()  # the CPU legs below run on rank 0 alone: no idle rank spins on the host cores
+    if rank != 0:
+        return
+
+    kernel_ms = float(kmax.item())
+    achieved_tf = acct[0] / (kernel_ms * 1e-3) / 1e12  # whole-job flops / slowest rank's kernel time
+    achieved_per_gpu = achieved_tf / world
+    cpu, parity = None, None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = min(m_count, args.cpu_sample or max(cores * CPU_SAMPLE_PER_CORE.get(args.workload, 16), 16))
+        # the CPU arm runs the FIRST `sample` sample indices of the same normals tensor / dual directions as rank 0's shard,
+        # so its per-trajectory results double as a parity check of the benchmarked run
+        rn_cpu = np.asfortranarray(rn_shard[:sample]) if m_begin == 0 else None
+        tput, dt, r = cpu_leg(args.workload, M, sample, cores, args.normals, rn_cpu if rn_cpu is not None else None, dd_full)
+        s1 = max(2, min(sample, sample // cores))
+        t1, dt1, _ = cpu_leg(args.workload, M, s1, 1, args.normals, rn_cpu, dd_full)
+        cpu = {"value": tput, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {sample} of {M} sample indices in {dt:.1f} s (oracle/rbo_oracle.cpp = C++/OpenMP restatement of the reference; Julia not installed)",
+               "single_thread": {"value": t1, "unit": UNIT, "sample": f"first {s1} sample indices in {dt1:.1f} s, 1 thread (the reference itself is serial, rollout.jl:293)"}}
+        ev = np.abs(gpu_vals[:sample] - r["values"]) / np.maximum(1.0, np.abs(r["values"]))
+        parity = {"n": int(sample), "max_rel_err_values": float(ev.max()), "frac_values_within_1e-8": float(np.mean(ev <= 1e-8))}
+        if want_grad:
+            gsc = np.maximum(np.abs(r["grad_x"]).max(axis=0), 1e-6)
+            eg = np.abs(gpu_gx[:, :sample] - r["grad_x"]).max(axis=0) / gsc
+            parity.update({"frac_grad_within_1e-5": float(np.mean(eg <= 1e-5)), "max_rel_err_grad": float(eg.max())})
+        parity["ok"] = bool(parity["frac_values_within_1e-8"] >= 0.98 and parity.get("frac_grad_within_1e-5", 1.0) >= 0.97)
+    traffic = TRAFFIC_NCU.get(args.workload) if (args.M is None and world == 1) else None
+    line = {
+        "metric": METRIC if want_grad else "rollout trajectories/sec (value only)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(wl, args.normals, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
+                "steps": e2e_steps, "all_trajectories_ok": ok_e2e, "host_breakdown_ms": brk},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "tensor", "pipe": "FP64 (mma.sync.m8n8k4.f64 and DFMA share the same 64 FMA/clk/SM)", "achieved": achieved_per_gpu, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_per_gpu / peak_tf,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload (1 GPU), from the ncu
+                     # capture named in traffic_source
+                     "traffic": traffic[0] if traffic else None,
+                     "traffic_unit": "bytes per launch", "traffic_source": traffic[1] if traffic else None,
+                     "kernel": "rbo_rollout_kernel_largen" if args.workload == "C5" else "rbo_rollout_kernel", "kernel_ms": kernel_ms,
+                     "flops_per_launch": acct[0] / world, "flops_executed_per_launch": acct[1] / world,
+                     "frac_executed": acct[1] / world / (kernel_ms * 1e-3) / 1e12 / peak_tf,
+                     "peak_source": "rbo_fp64_peak: dense FP64 FMA micro-benchmark in this process (MEASURED_PEAKS.json has no FP64 figure)",
+                     "kernel_share_of_step": kernel_ms / ms_per_step},
+        "cpu_baseline": cpu,
+        "parity_in_bench": parity,
+        "estimate": {"mean": mean_v, "std": std_v, "grad_x_mean": gm.tolist(), "n_failed": int(acct[3]),
+                     "acquisition_evals_per_trajectory": acct[2] / M},
+    }
+    if sga_info:
+        line["sga_loop"] = sga_info
+    print(json.dumps(line), flush=True)
+    if parity is not None and not parity["ok"]:
+        print("bench.py: parity_in_bench FAILED: " + json.dumps(parity), file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":
