@@ -224,7 +224,7 @@ def main():
     eng.set_starts(starts)
     rn_shard = eng.get_normals(h + 1)  # host copy of this rank's normals for the e2e arm (m_count x (d+1) x (h+1))
 
-    nsum = 1 + 3 * (1 + d + 1)
+    nsum = 1 + 3 * (1 + d + 1) + 2  # rows, then [n_failed, watchdog]: they travel through the same all-reduce
     sums = torch.zeros(nsum, dtype=torch.float64, device=dev)
     sums_pin = torch.empty(nsum, dtype=torch.float64, pin_memory=True)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)

@@ -116,6 +116,15 @@ int rbo_set_surrogate(rbo_handle* h, int d, int N, const double* X, int ldX, con
                       const double* y, const double* c, double sigma_n2, int kernel_id, const double* ktheta,
                       int nktheta, int rule_id, double sigma_tol);
 
+/* condition!(s::Surrogate, x, y) (rbs.jl:214-222) on the RESIDENT surrogate: appends the observation (x[d], y), extends the
+ * kernel-matrix row (update_covariance!, rbs.jl:166-183), the factor by one row (update_cholesky!, rbs.jl:185-203: here the
+ * matching row of L0^-1) and re-solves the coefficients (update_coefficients!, rbs.jl:205-212), all on the device: the factor
+ * never returns to the host between Bayesian-optimisation iterations. RBO_ERR_NUMERIC where the reference would throw
+ * PosDefException; the resident surrogate is then unchanged. Normals, starts and quadrature data stay valid. */
+int rbo_condition(rbo_handle* h, const double* x, double y);
+/* Reads the resident surrogate back (any pointer may be NULL): N, X (d x N, ldX >= d), y[N], c[N] = K^-1 y. */
+int rbo_get_surrogate(rbo_handle* h, int* N, double* X, int ldX, double* y, double* c);
+
 /* tp.rnstream_sequence (trajectory.jl:47): M_total x (d+1) x hp1, column-major, sample index fastest.
  * This handle keeps samples [m_begin, m_begin + m_count). */
 int rbo_set_normals(rbo_handle* h, const double* rn, int M_total, int hp1, int m_begin, int m_count);
@@ -141,7 +150,8 @@ int rbo_set_starts(rbo_handle* h, const double* starts, int S);
  *                             indexed [k, solve_index, m]; NULL = zeros. Only read in VALUE_GRAD mode.
  *   x_forced                : d x horizon x m_count, only with RBO_FLAG_TEACHER_FORCED
  *   values[m_count]         : resolutions (rollout.jl:318)
- *   grad_x[d x m_count], grad_theta[ntheta x m_count] : the gradient containers (rollout.jl:321-322), may be NULL
+ *   grad_x[d x m_count], grad_theta[ntheta x m_count] : the gradient containers (rollout.jl:321-322); both required in
+ *                             RBO_MODE_VALUE_GRAD (RBO_ERR_ARG otherwise), ignored in RBO_MODE_VALUE
  *   best_index, grad_case, status : int32[m_count], may be NULL (t of rollout.jl:235; case 1/2/3 of :239-251)
  *   summary                 : may be NULL
  */
@@ -160,18 +170,21 @@ int rbo_rollout_batch(rbo_handle* h, const double* x0s, int n_x0, const double* 
                       double fmini, int mode, const double* dual_dirs, double* values, double* grad_x, double* grad_theta, int32_t* status,
                       rbo_summary* summary);
 /* Same computation, results left on the device (no per-trajectory D2H): only x0 (d doubles) goes in and the
- * partial sums come out through rbo_get_partial_sums. Used by the SGA loop and by bench.py's device-resident
+ * partial sums come out through rbo_partial_sums_device. Used by the SGA loop and by bench.py's device-resident
  * timing. dual_dirs_device / x_forced_device are device pointers or NULL. */
 int rbo_rollout_device(rbo_handle* h, const double* x0, const double* theta, int ntheta, const double* lbs,
                        const double* ubs, int horizon, double fmini, int mode, int flags,
                        const double* dual_dirs_device, const double* x_forced_device, rbo_summary* summary);
 
 /* Per-handle partial statistics of the last rollout, for the multi-GPU all-reduce:
- * sums = [n, n*mean_v, M2_v, n*mean_v^2, (n*mean, M2, n*mean^2) per grad_x row..., per grad_theta row...]
- * length 1 + 3*(1 + d + ntheta). Written to a DEVICE buffer (e.g. a torch tensor handed to NCCL).
+ * sums = [n, n*mean_v, M2_v, n*mean_v^2, (n*mean, M2, n*mean^2) per grad_x row..., per grad_theta row..., n_failed, watchdog]
+ * length 1 + 3*(1 + d + ntheta) + 2. Written to a DEVICE buffer (e.g. a torch tensor handed to NCCL), stream-ordered.
+ * n counts the trajectories with status RBO_TRAJ_OK only -- failed ones are excluded from every sum and counted in n_failed;
+ * watchdog != 0 if the kernel reported a stuck pipeline or an inner solve beyond its evaluation bound.
  * M2 is the centred sum of squares around this handle's own mean (two-pass, as rollout.jl:328-337). */
 int rbo_partial_sums_device(rbo_handle* h, double* sums_device, int len);
-/* Host-side merge of all-reduced sums into means / corrected sample stds (Chan's pairwise update). */
+/* Host-side merge of all-reduced sums into means / corrected sample stds (Chan's pairwise update). Returns RBO_ERR_NUMERIC
+ * when any rank reported a failed trajectory or a watchdog flag (the reference would have thrown): no silent estimates. */
 int rbo_finalize_sums(const double* sums, int d, int ntheta, double* mean, double* std, double* gx_mean,
                       double* gx_std, double* gth_mean, double* gth_std);
 

@@ -37,6 +37,8 @@ SYMBOLS = {
     "rbo_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "rbo_set_surrogate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _dp, C.c_double, C.c_int,
                                     _dp, C.c_int, C.c_int, C.c_double]),
+    "rbo_condition": (C.c_int, [C.c_void_p, _dp, C.c_double]),
+    "rbo_get_surrogate": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), _dp, C.c_int, _dp, _dp]),
     "rbo_set_normals": (C.c_int, [C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "rbo_generate_normals": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "rbo_get_normals": (C.c_int, [C.c_void_p, _dp]),

@@ -434,6 +434,19 @@ class RolloutEngine:
                                                      fs.σn2, fs.ψ.kernel_id, dptr(kt), len(kt), fs.g.rule_id, fs.g.σtol))
         self.d = d
 
+    def condition(self, xnew, ynew):
+        """condition!(s::Surrogate, x, y) (rbs.jl:214-222) on the device-resident surrogate (rbo_condition)."""
+        x = np.ascontiguousarray(xnew, dtype=np.float64)
+        self.handle.check(self.lib.rbo_condition(self.handle.h, dptr(x), float(ynew)))
+
+    def get_surrogate(self):
+        """The resident surrogate: X (d x N), y, c = K^-1 y."""
+        n = C.c_int()
+        self.handle.check(self.lib.rbo_get_surrogate(self.handle.h, C.byref(n), None, 0, None, None))
+        X = np.zeros((self.d, n.value), order="F"); y = np.zeros(n.value); c = np.zeros(n.value)
+        self.handle.check(self.lib.rbo_get_surrogate(self.handle.h, C.byref(n), dptr(X), self.d, dptr(y), dptr(c)))
+        return X, y, c
+
     def set_normals(self, rn, m_begin=0, m_count=None):
         rn = np.asfortranarray(rn, dtype=np.float64)
         M = rn.shape[0]

@@ -22,6 +22,17 @@ __global__ void rbo_sobol_kernel(const unsigned* dirs, unsigned* out_u32, double
 __global__ void rbo_stats_kernel(const double* values, const double* gx, const double* gth, const int* n_evals, const int* best_index, const int* grad_case,
                                  const int* status, int M, int d, int nth, int h, double* sums);
 __global__ void rbo_fp64_peak_kernel(double* out, int iters);
+__global__ void rbo_gather_sums_kernel(const double* sums, int need, int idx_failed, const int* work_counter, double* out);
+// surrogate_kernels.cu
+__global__ void rbo_trinv_kernel(const double* L, int N, int N32, double* Linv, int ldi);
+__global__ void rbo_pack_fwd_kernel(const double* Linv, int ldi, int nb32, double* Lf);
+__global__ void rbo_pack_bwd_kernel(const double* Linv, int ldi, int nb32, double* Lb, double* Lbf);
+__global__ void rbo_matvec_lower_kernel(const double* Linv, int ldi, int n, const double* v, double* out);
+__global__ void rbo_matvec_lower_t_kernel(const double* Linv, int ldi, int n, const double* v, double scale, double* out);
+__global__ void rbo_layout_x_kernel(const double* Xpts, int d, int N, int N8, double* Xb);
+__global__ void rbo_kvec_kernel(const double* Xpts, int d, int N, const double* x, KernelSpec kern, double* out);
+__global__ void rbo_dots_kernel(const double* l, const double* u, int n, double* scal);
+__global__ void rbo_append_row_kernel(double* Linv, int ldi, int n, const double* tmp, const double* scal, double kdiag, double ynew, double* u, int* status);
 }  // namespace rbo
 
 using namespace rbo;
@@ -67,6 +78,12 @@ struct rbo_handle {
   int vglob_wmax = 0;       // development knob: cap on the start slots of the large-n variant (0 = default)
   int force_vglob = 0;      // development / test knob: use the large-n variant even when shared memory would do
   double* Vscratch = nullptr, *Bscratch = nullptr;
+  // resident surrogate in its canonical device form (rbo_set_surrogate / rbo_condition): L0^-1 row-major with pitch ldi,
+  // the observation sites point-major, work vectors
+  double *Ld = nullptr, *Linv = nullptr, *Xpts = nullptr, *wk = nullptr;
+  int* dstat = nullptr;
+  size_t cap_Ld = 0, cap_Linv = 0, cap_Xpts = 0, cap_wk = 0;
+  int ldi = 0, cap_rows = 0;
   size_t cap_Vscratch = 0, cap_Bscratch = 0;
 };
 
@@ -162,7 +179,7 @@ int rbo_destroy(rbo_handle* h) {
   cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->Xb, h->yb, h->c0, h->u0, h->Lf, h->Lb, h->Lbf, h->x0_batch, h->rn, h->starts, h->sobol_dirs, h->values, h->grad_x, h->grad_theta, h->xs, h->ys,
                   h->gys, h->alphas, h->best_index, h->grad_case, h->status, h->n_evals, h->start_status, h->start_iters, h->work_counter, h->sums,
-                  h->dual_dirs, h->x_forced, h->cs_tape, h->gh_nodes, h->gh_weights, h->Vscratch, h->Bscratch};
+                  h->dual_dirs, h->x_forced, h->cs_tape, h->gh_nodes, h->gh_weights, h->Vscratch, h->Bscratch, h->Ld, h->Linv, h->Xpts, h->wk, h->dstat};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -201,6 +218,64 @@ int rbo_set_htol(rbo_handle* h, double htol) {
   return RBO_SUCCESS;
 }
 
+// (Re)packs everything the rollout kernel streams from the canonical device form (Linv, Xpts): Xb, Lf, Lb, Lbf. Stream-ordered.
+static int repack_surrogate(rbo_handle* h) {
+  const int N = h->N, d = h->d, BR = RBO_BR, LP = RBO_LP;
+  const int N8 = (N + RBO_PR - 1) / RBO_PR * RBO_PR, nb32 = (N + BR - 1) / BR;
+  h->N8 = N8; h->nb8 = N8 / RBO_PR; h->nb32 = nb32;
+  const size_t nchunks = (size_t)nb32 * (nb32 + 1) / 2, nLf = (size_t)LP * BR * nchunks, nLbf = (size_t)1024 * nchunks;
+  CK(h, dev_reserve(&h->Xb, &h->cap_Xb, (size_t)d * N8));
+  CK(h, dev_reserve(&h->Lf, &h->cap_Lf, nLf));
+  CK(h, dev_reserve(&h->Lb, &h->cap_Lb, nLf));
+  CK(h, dev_reserve(&h->Lbf, &h->cap_Lbf, nLbf));
+  CK(h, cudaMemsetAsync(h->Lf, 0, nLf * 8, h->stream));  // the 4 pad doubles per k
+  CK(h, cudaMemsetAsync(h->Lb, 0, nLf * 8, h->stream));
+  rbo_layout_x_kernel<<<(d * N8 + 255) / 256, 256, 0, h->stream>>>(h->Xpts, d, N, N8, h->Xb);
+  dim3 grid(8, nb32);
+  rbo_pack_fwd_kernel<<<grid, 256, 0, h->stream>>>(h->Linv, h->ldi, nb32, h->Lf);
+  rbo_pack_bwd_kernel<<<grid, 256, 0, h->stream>>>(h->Linv, h->ldi, nb32, h->Lb, h->Lbf);
+  CK(h, cudaGetLastError());
+  return RBO_SUCCESS;
+}
+
+// Capacity of the canonical form: rows_needed rows of L0^-1 (pitch = capacity, so that rbo_condition appends rows in place).
+static int reserve_surrogate(rbo_handle* h, int d, int rows_needed, bool keep) {
+  const int N32 = (rows_needed + RBO_BR - 1) / RBO_BR * RBO_BR;
+  if (N32 <= h->cap_rows && h->Linv && (size_t)rows_needed * d <= h->cap_Xpts) return RBO_SUCCESS;
+  const int cap = (rows_needed + 64 + RBO_BR - 1) / RBO_BR * RBO_BR;
+  double *nLinv = nullptr, *nX = nullptr;
+  CK(h, cudaMalloc((void**)&nLinv, (size_t)cap * cap * 8));
+  if (cudaMalloc((void**)&nX, (size_t)cap * d * 8) != cudaSuccess) { cudaFree(nLinv); return fail(h, RBO_ERR_CUDA, "reserve_surrogate: out of device memory"); }
+  cudaMemsetAsync(nLinv, 0, (size_t)cap * cap * 8, h->stream);
+  if (keep && h->Linv) {
+    const int rows = (h->N + RBO_BR - 1) / RBO_BR * RBO_BR;
+    cudaMemcpy2DAsync(nLinv, (size_t)cap * 8, h->Linv, (size_t)h->ldi * 8, (size_t)rows * 8, rows, cudaMemcpyDeviceToDevice, h->stream);
+    cudaMemcpyAsync(nX, h->Xpts, (size_t)h->N * d * 8, cudaMemcpyDeviceToDevice, h->stream);
+  }
+  cudaStreamSynchronize(h->stream);
+  if (h->Linv) cudaFree(h->Linv);
+  if (h->Xpts) cudaFree(h->Xpts);
+  h->Linv = nLinv; h->Xpts = nX; h->ldi = cap; h->cap_rows = cap; h->cap_Xpts = (size_t)cap * d; h->cap_Linv = (size_t)cap * cap;
+  // vectors that grow with the observation count
+  double *ny = nullptr, *nc = nullptr, *nu = nullptr;
+  if (cudaMalloc((void**)&ny, (size_t)cap * 8) != cudaSuccess || cudaMalloc((void**)&nc, (size_t)cap * 8) != cudaSuccess || cudaMalloc((void**)&nu, (size_t)cap * 8) != cudaSuccess)
+    return fail(h, RBO_ERR_CUDA, "reserve_surrogate: out of device memory");
+  cudaMemsetAsync(nc, 0, (size_t)cap * 8, h->stream); cudaMemsetAsync(nu, 0, (size_t)cap * 8, h->stream); cudaMemsetAsync(ny, 0, (size_t)cap * 8, h->stream);
+  if (keep && h->yb) {
+    cudaMemcpyAsync(ny, h->yb, (size_t)h->N * 8, cudaMemcpyDeviceToDevice, h->stream);
+    cudaMemcpyAsync(nc, h->c0, (size_t)h->N * 8, cudaMemcpyDeviceToDevice, h->stream);
+    cudaMemcpyAsync(nu, h->u0, (size_t)h->N * 8, cudaMemcpyDeviceToDevice, h->stream);
+  }
+  cudaStreamSynchronize(h->stream);
+  if (h->yb) cudaFree(h->yb);
+  if (h->c0) cudaFree(h->c0);
+  if (h->u0) cudaFree(h->u0);
+  h->yb = ny; h->c0 = nc; h->u0 = nu; h->cap_yb = h->cap_c0 = h->cap_u0 = (size_t)cap;
+  CK(h, dev_reserve(&h->wk, &h->cap_wk, (size_t)4 * cap + 64));
+  if (!h->dstat) CK(h, cudaMalloc((void**)&h->dstat, 4 * sizeof(int)));
+  return RBO_SUCCESS;
+}
+
 int rbo_set_surrogate(rbo_handle* h, int d, int N, const double* X, int ldX, const double* L, int ldL, const double* y, const double* c,
                       double sigma_n2, int kernel_id, const double* ktheta, int nktheta, int rule_id, double sigma_tol) {
   if (!h) return RBO_ERR_ARG;
@@ -209,101 +284,109 @@ int rbo_set_surrogate(rbo_handle* h, int d, int N, const double* X, int ldX, con
   if (kernel_id < RBO_KERNEL_MATERN12 || kernel_id > RBO_KERNEL_PERIODIC) return fail(h, RBO_ERR_ARG, "rbo_set_surrogate: unknown kernel id %d", kernel_id);
   if (rule_id < RBO_RULE_EI || rule_id > RBO_RULE_LCB) return fail(h, RBO_ERR_ARG, "rbo_set_surrogate: unknown decision rule id %d", rule_id);
   if (nktheta < 1 || nktheta > 4 || !ktheta) return fail(h, RBO_ERR_ARG, "rbo_set_surrogate: kernel hyper-parameters missing");
+  if ((size_t)N * 16 > 200 * 1024) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_set_surrogate: N = %d observations exceed the inversion kernel's shared-memory column (12800)", N);
   CK(h, cudaSetDevice(h->device));
-  const int N8 = (N + RBO_PR - 1) / RBO_PR * RBO_PR, nb8 = N8 / RBO_PR;
-  h->d = d; h->N = N; h->N8 = N8; h->nb8 = nb8;
+  if (d != h->d) {
+    // buffers laid out for another input dimension are no longer valid (normals are M x (d+1) x hp1, starts d x S, ...)
+    h->M = 0; h->hp1 = 0; h->S = 0; h->gh_M = 0; h->gh_depth = 0;
+    if (h->rn) { cudaFree(h->rn); h->rn = nullptr; h->cap_rn = 0; }
+    if (h->starts) { cudaFree(h->starts); h->starts = nullptr; h->cap_starts = 0; }
+    if (h->gh_nodes) { cudaFree(h->gh_nodes); h->gh_nodes = nullptr; h->cap_ghn = 0; }
+    if (h->gh_weights) { cudaFree(h->gh_weights); h->gh_weights = nullptr; h->cap_ghw = 0; }
+    h->cap_rows = 0;  // Xpts is sized with d
+  }
+  h->have_sur = false;
+  int rc = reserve_surrogate(h, d, N, false);
+  if (rc) return rc;
+  h->d = d; h->N = N;
   h->kern.id = kernel_id;
   for (int i = 0; i < 4; ++i) h->kern.th[i] = i < nktheta ? ktheta[i] : 0.0;
   h->rule_id = rule_id; h->sigma_tol = sigma_tol; h->sigma_n2 = sigma_n2;
   double a, b;
   kern_eval(h->kern, 0.0, h->k0, a, b);
   h->d2k0 = b;
-  // coordinate-major, padded base locations
-  std::vector<double> Xb((size_t)d * N8, 0.0), c0(N8, 0.0), u0(N8, 0.0);
-  for (int j = 0; j < N; ++j)
-    for (int p = 0; p < d; ++p) Xb[(size_t)p * N8 + j] = X[(size_t)j * ldX + p];
   double ymin = y[0];
-  for (int j = 0; j < N; ++j) { c0[j] = c[j]; ymin = std::min(ymin, y[j]); }
+  for (int j = 0; j < N; ++j) ymin = std::min(ymin, y[j]);
   h->ymin_base = ymin;
-  auto Lij = [&](int i, int k) -> double { return (i < N && k < N) ? L[(size_t)k * ldL + i] : (i == k ? 1.0 : 0.0); };
-  // u0 = L^-1 y (kept so that the coefficient re-solve of rbs.jl:422-429 only needs the backward half)
-  for (int i = 0; i < N; ++i) {
-    double s = y[i];
-    for (int k = 0; k < i; ++k) s -= Lij(i, k) * u0[k];
-    u0[i] = s / Lij(i, i);
-  }
-  // Explicit inverse of the base factor, in extended precision (one rounding per stored entry): every later
-  // "triangular solve" against L0 is then a dependency-free panel product on the FP64 tensor cores.
-  const int BR = RBO_BR, LP = RBO_LP, nb32 = (N + BR - 1) / BR, N32 = nb32 * BR;
-  h->nb32 = nb32;
-  std::vector<long double> Lr((size_t)N32 * N32, 0.0L), Li((size_t)N32 * N32, 0.0L);  // row-major L0 and L0^-1 (identity on the padding)
-  for (int i = 0; i < N32; ++i)
-    for (int k = 0; k <= i; ++k) Lr[(size_t)i * N32 + k] = Lij(i, k);
-  for (int i = 0; i < N32; ++i) {  // row i of the inverse: Li[i][:] = (e_i - sum_{k<i} L[i][k] Li[k][:]) / L[i][i]
-    long double* ri = Li.data() + (size_t)i * N32;
-    const long double* li = Lr.data() + (size_t)i * N32;
-    for (int k = 0; k < i; ++k) {
-      const long double lik = li[k];
-      if (lik == 0.0L) continue;
-      const long double* rk = Li.data() + (size_t)k * N32;
-      for (int j = 0; j <= k; ++j) ri[j] -= lik * rk[j];
-    }
-    ri[i] += 1.0L;
-    const long double dinv = 1.0L / li[i];
-    for (int j = 0; j <= i; ++j) ri[j] *= dinv;
-  }
-  auto Linv = [&](int i, int j) -> double { return (double)Li[(size_t)i * N32 + j]; };
-  // forward / backward 32-row panels of L0^-1, k-major with pitch RBO_LP, cut into 32-k chunks:
-  //   forward  panel ib (rows r0 = 32 ib ..): k = 0 .. r0 + 31                : Linv[r0 + r][k]        (v_I = sum_{J<=I} Linv[I][J] b_J)
-  //   backward panel ib: kk = 0 .. N32 - r0 - 33 : Linv[r0 + 32 + kk][r0 + r] ; then kk = 0..31 : Linv[r0 + kk][r0 + r]
-  //                                                                                                   (w_I = sum_{J>=I} Linv[J][I]' b_J)
-  const size_t nLf = (size_t)LP * BR * ((size_t)nb32 * (nb32 + 1) / 2), nLb = nLf;
-  std::vector<double> Lf(nLf, 0.0), Lb(nLb, 0.0);
-  for (int ib = 0; ib < nb32; ++ib) {
-    const int r0 = BR * ib;
-    double* pf = Lf.data() + (size_t)LP * BR * ((size_t)ib * (ib + 1) / 2);
-    for (int k = 0; k < r0 + BR; ++k)
-      for (int r = 0; r < BR; ++r) pf[(size_t)k * LP + r] = (k <= r0 + r) ? Linv(r0 + r, k) : 0.0;
-    double* pb = Lb.data() + (size_t)LP * BR * ((size_t)nb32 * ib - (size_t)ib * (ib - 1) / 2);
-    const int k0 = r0 + BR, nkb = N32 - k0;
-    for (int kk = 0; kk < nkb; ++kk)
-      for (int r = 0; r < BR; ++r) pb[(size_t)kk * LP + r] = Linv(k0 + kk, r0 + r);
-    for (int kk = 0; kk < BR; ++kk)
-      for (int r = 0; r < BR; ++r) pb[(size_t)(nkb + kk) * LP + r] = (kk >= r) ? Linv(r0 + kk, r0 + r) : 0.0;
-  }
-  // The backward panels once more in mma.m8n8k4 A-fragment order, for the pass that reads them straight from L2 (no staging):
-  // chunk (same order as Lb) -> 4 row-quarter tiles of 8 rows x 32 k -> 4 k-pairs -> lane (g = row, tg) -> {k = 8 p + tg, 8 p + 4 + tg}
-  const size_t nLbf = (size_t)1024 * ((size_t)nb32 * (nb32 + 1) / 2);
-  std::vector<double> Lbf(nLbf, 0.0);
-  for (int ib = 0; ib < nb32; ++ib) {
-    const int nc = nb32 - ib;
-    const double* pb = Lb.data() + (size_t)LP * BR * ((size_t)nb32 * ib - (size_t)ib * (ib - 1) / 2);
-    double* pf = Lbf.data() + (size_t)1024 * ((size_t)nb32 * ib - (size_t)ib * (ib - 1) / 2);
-    for (int cc = 0; cc < nc; ++cc)
-      for (int rq = 0; rq < 4; ++rq)
-        for (int pp = 0; pp < 4; ++pp)
-          for (int ln = 0; ln < 32; ++ln)
-            for (int e = 0; e < 2; ++e) {
-              const int g = ln >> 2, tg = ln & 3, k = cc * BR + 8 * pp + 4 * e + tg;
-              pf[(((size_t)cc * 4 + rq) * 4 + pp) * 64 + 2 * ln + e] = pb[(size_t)k * LP + 8 * rq + g];
-            }
-  }
-  CK(h, dev_reserve(&h->Xb, &h->cap_Xb, Xb.size()));
-  CK(h, dev_reserve(&h->yb, &h->cap_yb, (size_t)N));
-  CK(h, dev_reserve(&h->c0, &h->cap_c0, (size_t)N8));
-  CK(h, dev_reserve(&h->u0, &h->cap_u0, (size_t)N8));
-  CK(h, dev_reserve(&h->Lf, &h->cap_Lf, nLf));
-  CK(h, dev_reserve(&h->Lb, &h->cap_Lb, nLb));
-  CK(h, dev_reserve(&h->Lbf, &h->cap_Lbf, nLbf));
-  CK(h, cudaMemcpyAsync(h->Xb, Xb.data(), Xb.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  const int N32 = (N + RBO_BR - 1) / RBO_BR * RBO_BR;
+  // H2D of what FantasySurrogate(s, h) copies (rbs.jl:345-381): X (d x N), the lower factor, y, c
+  CK(h, dev_reserve(&h->Ld, &h->cap_Ld, (size_t)N * N));
+  CK(h, cudaMemcpy2DAsync(h->Xpts, (size_t)d * 8, X, (size_t)ldX * 8, (size_t)d * 8, N, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpy2DAsync(h->Ld, (size_t)N * 8, L, (size_t)ldL * 8, (size_t)N * 8, N, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemsetAsync(h->c0, 0, h->cap_c0 * 8, h->stream));
+  CK(h, cudaMemsetAsync(h->u0, 0, h->cap_u0 * 8, h->stream));
   CK(h, cudaMemcpyAsync(h->yb, y, (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->c0, c0.data(), (size_t)N8 * 8, cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->u0, u0.data(), (size_t)N8 * 8, cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->Lf, Lf.data(), nLf * 8, cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->Lb, Lb.data(), nLb * 8, cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->Lbf, Lbf.data(), nLbf * 8, cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));  // the staging vectors die here
+  CK(h, cudaMemcpyAsync(h->c0, c, (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
+  // Explicit inverse of the base factor on the device in double-double arithmetic (one rounding per stored entry): every later
+  // "triangular solve" against L0 is then a dependency-free panel product on the FP64 tensor cores.
+  CK(h, cudaMemsetAsync(h->Linv, 0, (size_t)N32 * h->ldi * 8, h->stream));
+  {
+    const int wpc = std::max(1, std::min(4, (int)((200 * 1024) / ((size_t)N * 16))));
+    const size_t smem = (size_t)wpc * 2 * N * 8;
+    CK(h, cudaFuncSetAttribute(rbo_trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    rbo_trinv_kernel<<<(N32 + wpc - 1) / wpc, 32 * wpc, smem, h->stream>>>(h->Ld, N, N32, h->Linv, h->ldi);
+    CK(h, cudaGetLastError());
+  }
+  // u0 = L^-1 y (kept so that the coefficient re-solve of rbs.jl:422-429 only needs the backward half)
+  rbo_matvec_lower_kernel<<<(N + 7) / 8, 256, 0, h->stream>>>(h->Linv, h->ldi, N, h->yb, h->u0);
+  CK(h, cudaGetLastError());
+  rc = repack_surrogate(h);
+  if (rc) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));  // the caller's buffers may change after return
   h->have_sur = true;
+  return RBO_SUCCESS;
+}
+
+int rbo_condition(rbo_handle* h, const double* x, double y) {
+  if (!h || !x) return RBO_ERR_ARG;
+  if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_condition: no surrogate (rbo_set_surrogate)");
+  CK(h, cudaSetDevice(h->device));
+  const int n = h->N, d = h->d;
+  if ((size_t)(n + 1) * 16 > 200 * 1024) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_condition: too many observations");
+  int rc = reserve_surrogate(h, d, n + 1, true);
+  if (rc) return rc;
+  double* kv = h->wk; double* lv = kv + h->cap_rows; double* tmp = lv + h->cap_rows; double* scal = tmp + h->cap_rows; double* xd = scal + 8;
+  CK(h, cudaMemcpyAsync(xd, x, (size_t)d * 8, cudaMemcpyHostToDevice, h->stream));
+  if (n % RBO_BR == 0) {
+    // the factor grows by a panel: its padding rows are the identity
+    std::vector<double> one(1, 1.0);
+    CK(h, cudaMemsetAsync(h->Linv + (size_t)n * h->ldi, 0, (size_t)RBO_BR * h->ldi * 8, h->stream));
+    for (int r = n + 1; r < n + RBO_BR; ++r) CK(h, cudaMemcpyAsync(h->Linv + (size_t)r * h->ldi + r, one.data(), 8, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+  }
+  // update_covariance! (rbs.jl:166-183): k = psi(|x - X_j|); update_cholesky! (rbs.jl:185-203): l = L^-1 k, l_nn = sqrt(k0 + sigma_n2 - l.l)
+  rbo_kvec_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->Xpts, d, n, xd, h->kern, kv);
+  rbo_matvec_lower_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(h->Linv, h->ldi, n, kv, lv);
+  rbo_dots_kernel<<<1, 32, 0, h->stream>>>(lv, h->u0, n, scal);
+  rbo_matvec_lower_t_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->Linv, h->ldi, n, lv, 1.0, tmp);
+  rbo_append_row_kernel<<<(n + 256) / 256, 256, 0, h->stream>>>(h->Linv, h->ldi, n, tmp, scal, h->k0 + h->sigma_n2, y, h->u0, h->dstat);
+  CK(h, cudaGetLastError());
+  int st = 0;
+  CK(h, cudaMemcpyAsync(&st, h->dstat, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (st != 0) return fail(h, RBO_ERR_NUMERIC, "rbo_condition: PosDefException -- the extended kernel matrix is not positive definite (rbs.jl:196)");
+  CK(h, cudaMemcpyAsync(h->Xpts + (size_t)n * d, xd, (size_t)d * 8, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->yb + n, &y, 8, cudaMemcpyHostToDevice, h->stream));
+  h->N = n + 1;
+  h->ymin_base = std::min(h->ymin_base, y);
+  // update_coefficients! (rbs.jl:205-212): c = L^-T (L^-1 y), a full re-solve in the reference as well
+  rbo_matvec_lower_t_kernel<<<(n + 1 + 127) / 128, 128, 0, h->stream>>>(h->Linv, h->ldi, n + 1, h->u0, 1.0, h->c0);
+  CK(h, cudaGetLastError());
+  rc = repack_surrogate(h);
+  if (rc) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return RBO_SUCCESS;
+}
+
+int rbo_get_surrogate(rbo_handle* h, int* N_out, double* X, int ldX, double* y, double* c) {
+  if (!h) return RBO_ERR_ARG;
+  if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_get_surrogate: no surrogate");
+  CK(h, cudaSetDevice(h->device));
+  if (N_out) *N_out = h->N;
+  if (X) { if (ldX < h->d) return fail(h, RBO_ERR_ARG, "rbo_get_surrogate: ldX < d"); CK(h, cudaMemcpy2DAsync(X, (size_t)ldX * 8, h->Xpts, (size_t)h->d * 8, (size_t)h->d * 8, h->N, cudaMemcpyDeviceToHost, h->stream)); }
+  if (y) CK(h, cudaMemcpyAsync(y, h->yb, (size_t)h->N * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (c) CK(h, cudaMemcpyAsync(c, h->c0, (size_t)h->N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
   return RBO_SUCCESS;
 }
 
@@ -379,6 +462,7 @@ int rbo_set_starts(rbo_handle* h, const double* starts, int S) {
 static int ensure_outputs(rbo_handle* h, int M, int hor, int S, int d, int nth) {
   if (h->outM == M && h->outh == hor && h->outS == S && h->outd == d && h->outnth == nth) return RBO_SUCCESS;
   const int hh = std::max(hor, 1);
+  h->outM = 0; h->outh = -1;  // the cache key is only valid once every buffer below exists
   CK(h, dev_realloc(&h->values, (size_t)M));
   CK(h, dev_realloc(&h->grad_x, (size_t)M * d));
   CK(h, dev_realloc(&h->grad_theta, (size_t)M * nth));
@@ -527,7 +611,7 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
     const int d = h->d, hh = std::max(horizon, 1), nrows = 1 + d + ntheta;
     const double n = sums[0];
     summary->n_traj = M;
-    summary->mean = sums[1] / n;
+    summary->mean = n > 0 ? sums[1] / n : NAN;
     summary->std = n > 1 ? std::sqrt(sums[2] / (n - 1)) : NAN;
     summary->kernel_ms = ms;
     summary->gpu_launches = 2;
@@ -638,15 +722,21 @@ int rbo_rollout_batch(rbo_handle* h, const double* x0s, int n_x0, const double* 
 int rbo_partial_sums_device(rbo_handle* h, double* sums_device, int len) {
   if (!h || !sums_device) return RBO_ERR_ARG;
   const int need = 1 + 3 * (1 + h->outd + h->outnth);
-  if (!h->sums || len < need) return fail(h, RBO_ERR_ARG, "rbo_partial_sums_device: need %d doubles", need);
+  if (!h->sums || len < need + 2) return fail(h, RBO_ERR_ARG, "rbo_partial_sums_device: need %d doubles (1 + 3 (1 + d + ntheta) + 2)", need + 2);
   CK(h, cudaSetDevice(h->device));
-  CK(h, cudaMemcpyAsync(sums_device, h->sums, (size_t)need * 8, cudaMemcpyDeviceToDevice, h->stream));
+  const int hh = std::max(h->outh, 1);
+  const int idx_failed = need + hh + (h->outh + 2);  // sums layout of rbo_stats_kernel: rows, evaluations per step, case-3 histogram, failures
+  rbo_gather_sums_kernel<<<1, 64, 0, h->stream>>>(h->sums, need, idx_failed, h->work_counter, sums_device);
+  CK(h, cudaGetLastError());
   return RBO_SUCCESS;
 }
 
 int rbo_finalize_sums(const double* sums, int d, int ntheta, double* mean, double* std_, double* gx_mean, double* gx_std, double* gth_mean, double* gth_std) {
   if (!sums) return RBO_ERR_ARG;
   const double n = sums[0];
+  const int need = 1 + 3 * (1 + d + ntheta);
+  // a failed trajectory (where the reference would have thrown) or a kernel watchdog flag on ANY rank poisons the estimate
+  if (sums[need] > 0.0 || sums[need + 1] > 0.0) return RBO_ERR_NUMERIC;
   if (!(n > 0)) return RBO_ERR_ARG;
   for (int row = 0; row < 1 + d + ntheta; ++row) {
     const double sm = sums[1 + 3 * row], m2 = sums[2 + 3 * row], smm = sums[3 + 3 * row];
@@ -683,6 +773,7 @@ static int sobol_common(rbo_handle* h, int dim, int npoints, uint32_t* out_u32, 
   CK(h, cudaSetDevice(h->device));
   const size_t total = (size_t)dim * npoints;
   unsigned* du = nullptr; double* df = nullptr; double* db = nullptr;
+  struct Guard { unsigned*& a; double*& b; double*& c; ~Guard() { if (a) cudaFree(a); if (b) cudaFree(b); if (c) cudaFree(c); } } guard{du, df, db};  // temporaries die on every path
   if (out_u32) CK(h, cudaMalloc((void**)&du, total * 4));
   if (out_f64) CK(h, cudaMalloc((void**)&df, total * 8));
   if (lbs) {
@@ -696,9 +787,6 @@ static int sobol_common(rbo_handle* h, int dim, int npoints, uint32_t* out_u32, 
   if (out_u32) CK(h, cudaMemcpyAsync(out_u32, du, total * 4, cudaMemcpyDeviceToHost, h->stream));
   if (out_f64) CK(h, cudaMemcpyAsync(out_f64, df, total * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
-  if (du) cudaFree(du);
-  if (df) cudaFree(df);
-  if (db) cudaFree(db);
   return RBO_SUCCESS;
 }
 
@@ -745,6 +833,7 @@ int rbo_fp64_peak(rbo_handle* h, double* tflops) {
   CK(h, cudaSetDevice(h->device));
   const int blocks = h->num_sms * 4, threads = 512, iters = 4096;
   double* out = nullptr;
+  struct Guard { double*& p; ~Guard() { if (p) cudaFree(p); } } guard{out};
   CK(h, cudaMalloc((void**)&out, (size_t)blocks * threads * 8));
   double best = 0;
   for (int rep = 0; rep < 5; ++rep) {
@@ -757,7 +846,6 @@ int rbo_fp64_peak(rbo_handle* h, double* tflops) {
     double fl = (double)blocks * threads * iters * 16.0 * 2.0;
     if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
   }
-  cudaFree(out);
   *tflops = best;
   return RBO_SUCCESS;
 }

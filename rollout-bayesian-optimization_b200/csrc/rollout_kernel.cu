@@ -1786,28 +1786,35 @@ __global__ void rbo_stats_kernel(const double* __restrict__ values, const double
     for (int w = 0; w < nw; ++w) tot += red[w];
     return tot;
   };
+  // trajectories that failed (status != 0: the reference would have thrown) are excluded from n and from
+  // every sum -- a half-factorised joint covariance yields finite garbage that must not leak into the estimate; their count is
+  // reported next to the sums and travels through the same all-reduce (rbo_partial_sums_device)
+  auto okay = [&](int i) { return !status || status[i] == 0; };
+  double nok_acc = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) nok_acc += okay(i) ? 1.0 : 0.0;
+  const double nok = block_sum(nok_acc);
   for (int row = 0; row < nrows; ++row) {
     const double* base; int stride;
     if (row == 0) { base = values; stride = 1; }
     else if (row <= d) { base = gx ? gx + (row - 1) : nullptr; stride = d; }
     else { base = gth ? gth + (row - 1 - d) : nullptr; stride = nth; }
     double mean = 0.0, m2 = 0.0;
-    if (base) {
+    if (base && nok > 0.0) {
       double acc = 0.0;
-      for (int i = threadIdx.x; i < M; i += blockDim.x) acc += base[(size_t)i * stride];
-      mean = block_sum(acc) / M;
+      for (int i = threadIdx.x; i < M; i += blockDim.x) if (okay(i)) acc += base[(size_t)i * stride];
+      mean = block_sum(acc) / nok;
       if (threadIdx.x == 0) s_mean = mean;
       __syncthreads();
       mean = s_mean;
       acc = 0.0;
-      for (int i = threadIdx.x; i < M; i += blockDim.x) { double v = base[(size_t)i * stride] - mean; acc += v * v; }
+      for (int i = threadIdx.x; i < M; i += blockDim.x) if (okay(i)) { double v = base[(size_t)i * stride] - mean; acc += v * v; }
       m2 = block_sum(acc);
     }
     if (threadIdx.x == 0) {
-      if (row == 0) sums[0] = (double)M;
-      sums[1 + 3 * row + 0] = M * mean;
+      if (row == 0) sums[0] = nok;
+      sums[1 + 3 * row + 0] = nok * mean;
       sums[1 + 3 * row + 1] = m2;
-      sums[1 + 3 * row + 2] = M * mean * mean;
+      sums[1 + 3 * row + 2] = nok * mean * mean;
     }
   }
   const int hh = h > 1 ? h : 1;
@@ -1828,6 +1835,12 @@ __global__ void rbo_stats_kernel(const double* __restrict__ values, const double
     double tot = block_sum(acc);
     if (threadIdx.x == 0) hist[t + (t > h ? 1 : 0)] = tot;
   }
+}
+
+// out = [sums[0 .. need), number of failed trajectories, kernel watchdog flag]: the vector the multi-GPU all-reduce sums
+__global__ void rbo_gather_sums_kernel(const double* __restrict__ sums, int need, int idx_failed, const int* __restrict__ work_counter, double* __restrict__ out) {
+  for (int i = threadIdx.x; i < need; i += blockDim.x) out[i] = sums[i];
+  if (threadIdx.x == 0) { out[need] = sums[idx_failed]; out[need + 1] = (work_counter[1] || work_counter[2]) ? 1.0 : 0.0; }
 }
 
 // FP64 FMA micro-benchmark: the roofline denominator for this path (MEASURED_PEAKS.json has no FP64 figure).

@@ -653,3 +653,73 @@ def test_free_running_parity_at_baseline_shapes(pkg, orc, name, kw, npick):
         assert np.array_equal(a["grad_case"][same], ref["grad_case"][same])
         gscale = np.maximum(np.abs(ref["grad_x"]).max(axis=0, keepdims=True), 1e-6)
         assert np.mean(np.max(np.abs(a["grad_x"] - ref["grad_x"]) / gscale, axis=0) < 1e-5) >= 0.97
+
+
+def test_condition_on_device_matches_host_refit(pkg, orc):
+    """rbo_condition (condition!(::Surrogate), rbs.jl:214-222, on the resident surrogate: kernel row, one more row of L0^-1,
+    coefficient re-solve, repack) against a host refit of the extended data set: coefficients and a teacher-forced rollout.
+    Crosses a 32-row panel boundary (N = 62 -> 67) and an 8-row boundary."""
+    d, N, h, M, S = 4, 62, 2, 24, 3
+    sur, P, rn, starts, dd, lbs, ubs, x0 = custom_case(pkg, orc, d, N, h, M, S, "Matern52", (0.5,), "EI", (0.0,))
+    rng = np.random.default_rng(9)
+    newx = rng.random((d, 5)); newy = rng.standard_normal(5) * 0.3
+    eng = pkg.RolloutEngine(0)
+    try:
+        eng.set_surrogate(pkg.FantasySurrogate(sur, h))
+        eng.set_normals(rn); eng.set_starts(starts)
+        Xh, yh = sur.X[:, :N].copy(), sur.y[:N].copy()
+        for j in range(5):
+            eng.condition(newx[:, j], newy[j])
+            Xh = np.concatenate([Xh, newx[:, j:j + 1]], axis=1); yh = np.append(yh, newy[j])
+        Xd, yd, cd = eng.get_surrogate()
+        assert Xd.shape[1] == N + 5 and np.array_equal(Xd, Xh) and np.array_equal(yd, yh)
+        ref_sur = pkg.Surrogate(pkg.Matern52([0.5]), Xh, yh, capacity=N + 8, decision_rule=pkg.EI(), σn2=1e-6)
+        assert relerr(cd, ref_sur.c[:N + 5], floor=np.abs(ref_sur.c[:N + 5]).max()) < 1e-9
+        # the same rollout through the conditioned handle and through a handle that received the host refit
+        vals, gx, gt, st = np.zeros(M), np.zeros((d, M), order="F"), np.zeros((1, M), order="F"), np.zeros(M, np.int32)
+        fmini = float(np.min(yh))
+        eng.rollout(x0, np.zeros(1), lbs, ubs, h, fmini, vals, gx, gt, dual_dirs=dd, status=st)
+        xs = eng.tape(h)["xs"]
+        eng2 = pkg.RolloutEngine(0)
+        try:
+            eng2.set_surrogate(pkg.FantasySurrogate(ref_sur, h)); eng2.set_normals(rn); eng2.set_starts(starts)
+            v2, g2, t2, s2 = np.zeros(M), np.zeros((d, M), order="F"), np.zeros((1, M), order="F"), np.zeros(M, np.int32)
+            eng2.rollout(x0, np.zeros(1), lbs, ubs, h, fmini, v2, g2, t2, dual_dirs=dd, x_forced=np.asfortranarray(xs[:, 1:, :]), status=s2)
+        finally:
+            eng2.close()
+        assert np.all(st == 0) and np.all(s2 == 0) and relerr(vals, v2) < 1e-9
+        gscale = np.maximum(np.abs(g2).max(axis=0, keepdims=True), 1e-6)
+        assert np.max(np.abs(gx - g2) / gscale) < 1e-6
+        # and against the oracle on the extended data set
+        N_ = N + 5
+        P2 = orc.OracleProblem(ref_sur.X[:, :N_], ref_sur.L[:N_, :N_], ref_sur.y[:N_], ref_sur.c[:N_], x0, lbs, ubs, rn, starts, h=h, kernel="matern52",
+                               ktheta=(0.5,), rule="EI", theta=(0.0,), sigma_n2=1e-6, fmini=fmini, mode=1, dual_dirs=dd, x_forced=np.asfortranarray(xs[:, 1:, :]))
+        r = P2.rollout()
+        assert relerr(vals, r["values"]) < 1e-8
+    finally:
+        eng.close()
+
+
+def test_failed_trajectories_poison_the_device_resident_estimate(pkg, orc):
+    """The device-resident path (rbo_rollout_device + rbo_partial_sums_device + rbo_finalize_sums, what the multi-GPU all-reduce
+    and the SGA loop use) must not return a silent estimate when a trajectory failed where the reference would have thrown:
+    Matern-1/2 makes the joint value/gradient covariance indefinite on every sample (rbs.jl:537)."""
+    import ctypes as C
+    d, N, h, M, S = 3, 18, 2, 16, 3
+    sur, P, rn, starts, dd, lbs, ubs, x0 = custom_case(pkg, orc, d, N, h, M, S, "Matern12", (0.6,), "EI", (0.01,))
+    eng = pkg.RolloutEngine(0)
+    try:
+        eng.set_surrogate(pkg.FantasySurrogate(sur, h)); eng.set_normals(rn); eng.set_starts(starts)
+        eng.rollout_device(x0, np.array([0.01]), lbs, ubs, h, float(np.min(sur.y)), 0)
+        import torch
+        nsum = 1 + 3 * (1 + d + 1) + 2
+        sums = torch.zeros(nsum, dtype=torch.float64, device="cuda:0")
+        eng.handle.check(eng.lib.rbo_partial_sums_device(eng.handle.h, C.c_void_p(sums.data_ptr()), nsum))
+        torch.cuda.synchronize()
+        host = sums.cpu().numpy()
+        assert host[-2] == M and host[0] == 0  # every trajectory failed, none is counted
+        m = C.c_double()
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        assert eng.lib.rbo_finalize_sums(p(host), d, 1, C.byref(m), None, None, None, None, None) == -5
+    finally:
+        eng.close()

@@ -83,7 +83,7 @@ def test_finalize_sums_merges_shards(pkg):
     rng = np.random.default_rng(3)
     d, nth = 3, 1
     shards = [rng.standard_normal((1 + d + nth, n)) + 2.0 for n in (5, 11, 8)]
-    tot = np.zeros(1 + 3 * (1 + d + nth))
+    tot = np.zeros(1 + 3 * (1 + d + nth) + 2)  # ..., n_failed, watchdog
     for A in shards:
         n = A.shape[1]
         tot[0] += n
@@ -100,6 +100,10 @@ def test_finalize_sums_merges_shards(pkg):
     assert np.isclose(m.value, allA[0].mean()) and np.isclose(s.value, allA[0].std(ddof=1))
     assert np.allclose(gm, allA[1:1 + d].mean(axis=1)) and np.allclose(gs, allA[1:1 + d].std(axis=1, ddof=1))
     assert np.allclose(tm, allA[1 + d:].mean(axis=1)) and np.allclose(ts, allA[1 + d:].std(axis=1, ddof=1))
+    # a failed trajectory or a watchdog flag on any rank poisons the merged estimate: RBO_ERR_NUMERIC (-5), never a silent number
+    for idx in (-2, -1):
+        bad = tot.copy(); bad[idx] = 1.0
+        assert lib.rbo_finalize_sums(p(bad), d, nth, C.byref(m), C.byref(s), p(gm), p(gs), p(tm), p(ts)) == -5
 
 
 def test_bench_reference_arm_runs_on_cpu():

@@ -28,7 +28,7 @@ def _worker(rank, world, port, M, d, nth, ret):
     table = rng.standard_normal((1 + d + nth, M)) * 3.0 + 5.0
     b, n = shard(M, rank, world)
     mine = table[:, b:b + n]
-    sums = np.zeros(1 + 3 * (1 + d + nth))
+    sums = np.zeros(1 + 3 * (1 + d + nth) + 2)  # rows, then [n_failed, watchdog] (rbo_partial_sums_device)
     sums[0] = n
     for r in range(1 + d + nth):  # what rbo_stats_kernel writes per handle: [n*mean, M2, n*mean^2]
         mu = mine[r].mean()
@@ -49,7 +49,7 @@ def _worker(rank, world, port, M, d, nth, ret):
     dist.destroy_process_group()
 
 
-def test_two_rank_shard_and_merge():
+def test_two_rank_shard_and_merge(pkg):  # the `pkg` fixture builds librbo.so on a clean checkout before the workers load it
     world, M, d, nth = 2, 1001, 5, 1
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
