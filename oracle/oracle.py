@@ -69,6 +69,9 @@ def lib():
         _LIB.orc_generate_initial_guesses.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp]
         _LIB.orc_kernel_scalars.argtypes = [C.c_int, _dp, C.c_double, _dp]
         _LIB.orc_mean_std.argtypes = [_dp, C.c_int, C.c_int, _dp, _dp]
+        _LIB.orc_rule_partials.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _dp]
+        _LIB.orc_tr_step.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp]
+        _LIB.orc_tr_step.restype = C.c_int
     return _LIB
 
 
@@ -233,3 +236,18 @@ def mean_std(v):
     m, s = C.c_double(), C.c_double()
     lib().orc_mean_std(_ptr(v), len(v), 1, C.byref(m), C.byref(s))
     return m.value, s.value
+
+
+def rule_partials(rule, mu, sigma, theta1, fstar, sigma_tol=1e-8):
+    """[g, g_mu, g_sig, g_mumu, g_sigsig, g_muth, g_sigth, g_musig] of the C++ oracle's decision rule."""
+    out = np.zeros(8)
+    lib().orc_rule_partials(RULE_IDS[rule], sigma_tol, float(mu), float(sigma), float(theta1), float(fstar), _ptr(out))
+    return out
+
+
+def tr_step(H, g, Delta):
+    """Exact trust-region step of the oracle's inner solve: returns (p, hit_constraint)."""
+    H = np.ascontiguousarray(H, dtype=np.float64); g = _f(g)
+    p = np.zeros(len(g))
+    hit = lib().orc_tr_step(len(g), _ptr(H), _ptr(g), float(Delta), _ptr(p))
+    return p, bool(hit)

@@ -435,22 +435,6 @@ struct StartResult {
   int status, iters, evals;
 };
 
-bool chol_small(double* A, int n) {  // in place lower Cholesky, row-major, returns false if not PD
-  for (int j = 0; j < n; ++j) {
-    double s = A[j * n + j];
-    for (int k = 0; k < j; ++k) s -= A[j * n + k] * A[j * n + k];
-    if (!(s > 0) || !std::isfinite(s)) return false;
-    double ljj = std::sqrt(s);
-    A[j * n + j] = ljj;
-    for (int i = j + 1; i < n; ++i) {
-      double t = A[i * n + j];
-      for (int k = 0; k < j; ++k) t -= A[i * n + k] * A[j * n + k];
-      A[i * n + j] = t / ljj;
-    }
-  }
-  return true;
-}
-
 // ---- exact trust-region subproblem (solve_tr, optim.jl:9-51) without an eigendecomposition ------------------------
 // Householder tridiagonalisation H = Q T Q' (Golub & Van Loan 8.3.1), then every quantity of the secular equation
 // is an O(n) recurrence on T. The CUDA kernel runs the same steps with one warp (lane = row / candidate shift).
@@ -1271,6 +1255,17 @@ void orc_generate_initial_guesses(int S, int d, const double* lbs, const double*
   for (int a = 0; a < d; ++a) out[(size_t)(S + 1) * d + a] = ubs[a] - eps;
 }
 
+// decision-rule value and partials (decision_rules.jl:84-127), for the finite-difference ladder:
+// out = [g, g_mu, g_sig, g_mumu, g_sigsig, g_muth, g_sigth, g_musig]
+void orc_rule_partials(int rule_id, double sigma_tol, double mu, double sigma, double theta1, double fstar, double* out) {
+  const GPart g = rule_eval(rule_id, sigma_tol, mu, sigma, theta1, fstar);
+  out[0] = g.g; out[1] = g.g_mu; out[2] = g.g_sig; out[3] = g.g_mumu; out[4] = g.g_sigsig; out[5] = g.g_muth; out[6] = g.g_sigth; out[7] = g.g_musig;
+}
+// the exact trust-region step of the inner solve (solve_tr, optim.jl:9-51): H n x n row-major symmetric; returns hit_constraint
+int orc_tr_step(int n, const double* H, const double* g, double Delta, double* p) {
+  std::vector<double> A(H, H + (size_t)n * n), work(8 * (size_t)n + 8);
+  return tr_step(A.data(), g, n, Delta, p, work.data()) ? 1 : 0;
+}
 void orc_kernel_scalars(int kernel_id, const double* ktheta, double rho, double* out) {
   Kern k;
   k.id = kernel_id;

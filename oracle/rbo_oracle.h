@@ -121,6 +121,10 @@ void orc_sobol_uint32(int dim, int npoints, unsigned* out /* dim x npoints col-m
 void orc_gen_low_discrepancy_sequence(int M, int d, int H, double* out);
 /* utils.jl:145-153: out is d x (S+2) */
 void orc_generate_initial_guesses(int S, int d, const double* lbs, const double* ubs, double* out);
+/* decision-rule value and partials: out = [g, g_mu, g_sig, g_mumu, g_sigsig, g_muth, g_sigth, g_musig] */
+void orc_rule_partials(int rule_id, double sigma_tol, double mu, double sigma, double theta1, double fstar, double* out);
+/* exact trust-region step of the inner solve (solve_tr, optim.jl:9-51); returns 1 when the constraint is active */
+int orc_tr_step(int n, const double* H, const double* g, double Delta, double* p);
 /* kernel scalar functions, for the FD ladder: out = [psi, dpsi, d2psi] */
 void orc_kernel_scalars(int kernel_id, const double* ktheta, double rho, double* out);
 

@@ -286,3 +286,134 @@ def test_oracle_reproduces_golden(orc, name):
         assert relerr(r[key], f[key]) < tol, key
     gscale = np.maximum(np.abs(f["grad_x"]).max(axis=0, keepdims=True), 1e-9)
     assert np.max(np.abs(r["grad_x"] - f["grad_x"]) / gscale) < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------------
+# Decision-rule partials of BOTH compiled implementations (the oracle's C++ and the product's rbo_device.cuh, the latter
+# built for the host) by centred finite differences -- the runtests.jl:11-20 idiom. Covers EI, POI, LCB including the
+# mixed partials g_mu_theta, g_sigma_theta, g_mu_sigma that only the adjoint / the solver's true Hessian consume.
+# ---------------------------------------------------------------------------------------------------
+def _device_scalars_lib():
+    import ctypes as C, os, subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, "helpers", "device_scalars.cu")
+    so = os.path.join(here, "helpers", "libdevice_scalars.so")
+    hdr = os.path.join(os.path.dirname(here), "rollout-bayesian-optimization_b200", "csrc", "rbo_device.cuh")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared", "-o", so, src])
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    lib.dev_rule_partials.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, dp]
+    lib.dev_kernel_scalars.argtypes = [C.c_int, dp, C.c_double, dp]
+    return lib
+
+
+def _rule_fn(which, orc):
+    if which == "oracle":
+        return lambda rule, mu, sg, th, fs: orc.rule_partials(rule, mu, sg, th, fs)
+    lib = _device_scalars_lib()
+    ids = {"EI": 0, "POI": 1, "LCB": 2}
+
+    def f(rule, mu, sg, th, fs):
+        out = np.zeros(8)
+        lib.dev_rule_partials(ids[rule], 1e-8, mu, sg, th, fs, out.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double)))
+        return out
+    return f
+
+
+@pytest.mark.parametrize("which", ["oracle", "product"])
+@pytest.mark.parametrize("rule", ["EI", "POI", "LCB"])
+def test_rule_partials_by_finite_differences(orc, which, rule):
+    f = _rule_fn(which, orc)
+    rng = np.random.default_rng(4)
+    for _ in range(12):
+        mu, sg, th, fs = rng.normal(0.2, 0.8), rng.uniform(0.05, 1.5), rng.uniform(0.0, 2.5) if rule == "LCB" else rng.uniform(0.0, 0.3), rng.normal(0.0, 0.6)
+        g, g_mu, g_sig, g_mumu, g_sigsig, g_muth, g_sigth, g_musig = f(rule, mu, sg, th, fs)
+        e = 1e-5
+        d = lambda i, k, dm=0.0, ds=0.0, dt=0.0: (f(rule, mu + dm, sg + ds, th + dt, fs)[i] - f(rule, mu - dm, sg - ds, th - dt, fs)[i]) / (2 * k)
+        sc = lambda v: max(1e-6, abs(v))
+        assert abs(d(0, e, dm=e) - g_mu) < 1e-7 * sc(g_mu) + 1e-9
+        assert abs(d(0, e, ds=e) - g_sig) < 1e-7 * sc(g_sig) + 1e-9
+        assert abs(d(1, e, dm=e) - g_mumu) < 1e-6 * sc(g_mumu) + 1e-8
+        assert abs(d(2, e, ds=e) - g_sigsig) < 1e-6 * sc(g_sigsig) + 1e-8
+        assert abs(d(1, e, ds=e) - g_musig) < 1e-6 * sc(g_musig) + 1e-8 and abs(d(2, e, dm=e) - g_musig) < 1e-6 * sc(g_musig) + 1e-8
+        assert abs(d(1, e, dt=e) - g_muth) < 1e-6 * sc(g_muth) + 1e-8
+        assert abs(d(2, e, dt=e) - g_sigth) < 1e-6 * sc(g_sigth) + 1e-8
+    # below sigma_tol EI and POI are the constant 0 with zero partials (decision_rules.jl:87-89, 104-106)
+    if rule != "LCB":
+        assert np.all(f(rule, 0.1, 1e-9, 0.0, 0.0) == 0.0)
+
+
+def test_product_kernel_scalars_by_finite_differences():
+    """psi', psi'' and the radial coefficients a = (psi'' - psi'/rho)/rho^2, b = psi'/rho of rbo_device.cuh (host build)."""
+    import ctypes as C
+    lib = _device_scalars_lib()
+    dp = C.POINTER(C.c_double)
+    for kid, th in ((0, [0.6, 0, 0, 0]), (1, [0.45, 0, 0, 0]), (2, [0.7, 0, 0, 0]), (3, [0.35, 0, 0, 0]), (4, [0.9, 1.7, 0, 0])):
+        kt = np.array(th, dtype=np.float64)
+        def ev(rho):
+            out = np.zeros(6)
+            lib.dev_kernel_scalars(kid, kt.ctypes.data_as(dp), rho, out.ctypes.data_as(dp))
+            return out
+        for rho in (0.123, 0.456, 1.3):
+            o, hh = ev(rho), 1e-6
+            assert abs((ev(rho + hh)[0] - ev(rho - hh)[0]) / (2 * hh) - o[1]) < 1e-7 * max(1.0, abs(o[1]))
+            assert abs((ev(rho + hh)[1] - ev(rho - hh)[1]) / (2 * hh) - o[2]) < 1e-6 * max(1.0, abs(o[2]))
+            assert np.isclose(o[4], o[1] / rho, rtol=1e-13) and np.isclose(o[3], (o[2] - o[1] / rho) / rho**2, rtol=1e-12) and o[5] == o[4]
+        o0 = ev(0.0)
+        assert o0[3] == 0.0 and o0[4] == o0[2] and o0[5] == 0.0  # rbf.jl:129-131, 149: grad k = 0, Hk = psi''(0) I at coincident points
+
+
+def _tr_exact(H, g, Delta):
+    w, Q = np.linalg.eigh(H)
+    gt = Q.T @ g
+    if w[0] > 0:
+        p = -Q @ (gt / w)
+        if np.linalg.norm(p) <= Delta:
+            return p
+    lo = max(0.0, -w[0])
+    f = lambda lam: np.linalg.norm(gt / (w + lam)) - Delta
+    hi = lo + np.linalg.norm(g) / Delta + 1.0
+    a, b = lo + 1e-14 * max(1.0, abs(lo)), hi
+    if f(a) < 0:  # hard case
+        y = np.where(w + lo > 1e-12 * max(abs(w).max(), 1e-300), -gt / np.where(w + lo > 1e-12, w + lo, 1.0), 0.0)
+        y[0] = np.sqrt(max(Delta**2 - y @ y + y[0] ** 2, 0.0))
+        return Q @ y
+    for _ in range(200):
+        m = 0.5 * (a + b)
+        if f(m) > 0: a = m
+        else: b = m
+    return -Q @ (gt / (w + b))
+
+
+def test_oracle_trust_region_step_is_exact(orc):
+    """orc_tr_step (Householder tridiagonalisation + 64-way multisection, the algorithm the CUDA warp runs as well) against a
+    dense eigendecomposition: feasibility, the model value of the exact minimiser, interior Newton steps, and the hard case."""
+    rng = np.random.default_rng(12)
+    model = lambda H, g, p: g @ p + 0.5 * p @ H @ p
+    for n in (1, 2, 3, 6, 10, 20, 31):
+        for trial in range(12):
+            A = rng.standard_normal((n, n)); H = 0.5 * (A + A.T)
+            if trial % 3 == 0:
+                H = A @ A.T + 0.1 * np.eye(n)      # positive definite
+            g = rng.standard_normal(n)
+            Delta = float(rng.choice([1e-3, 0.1, 1.0, 30.0]))
+            p, hit = orc.tr_step(H, g, Delta)
+            pe = _tr_exact(H, g, Delta)
+            assert np.linalg.norm(p) <= Delta * (1 + 1e-9)
+            scale = abs(model(H, g, pe)) + 1e-300
+            # the shift is located to 4e-6 of its initial bracket (3 rounds of 64-way multisection): |p| may fall short of Delta by
+            # a fraction of a percent when the shift sits just above -lambda_min -- immaterial for a trust-region method
+            assert model(H, g, p) <= model(H, g, pe) + 1e-2 * scale, (n, trial, model(H, g, p), model(H, g, pe))
+            if hit and n > 1:
+                assert np.linalg.norm(p) >= Delta * (1 - 1e-2)
+            if not hit:
+                assert np.allclose(H @ p, -g, rtol=1e-8, atol=1e-10) and np.all(np.linalg.eigvalsh(H) > 0)
+    # hard case: the gradient has no component along the eigenvector of the most negative eigenvalue
+    Q, _ = np.linalg.qr(rng.standard_normal((6, 6)))
+    w = np.array([-2.0, 0.5, 1.0, 1.5, 2.0, 3.0])
+    H = Q @ np.diag(w) @ Q.T; H = 0.5 * (H + H.T)
+    g = Q[:, 1:] @ rng.standard_normal(5) * 0.1
+    p, hit = orc.tr_step(H, g, 2.0)
+    pe = _tr_exact(H, g, 2.0)
+    assert hit and abs(np.linalg.norm(p) - 2.0) < 1e-6 and model(H, g, p) <= model(H, g, pe) + 1e-3 * abs(model(H, g, pe))
