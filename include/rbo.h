@@ -41,6 +41,8 @@ enum { RBO_MODE_VALUE = 0, RBO_MODE_VALUE_GRAD = 1 };
 /* flags */
 enum {
   RBO_FLAG_TEACHER_FORCED = 1, /* x_1..x_h supplied by the caller (step-level parity tests) */
+  RBO_FLAG_TAPE_EX = 4,        /* also record mu, sigma, grad mu, grad sigma, H alpha, alpha of the policy solve's surrogate evaluation at
+                                  every chosen x_j (one extra evaluation per step): rbo_get_tape_ex */
   RBO_FLAG_GAUSS_HERMITE = 2   /* simulate_trajectory_ghq (rollout.jl:409-467): GaussHermiteObservable draws (observables.jl:32-81,157)
                                   from the nodes / weights of rbo_set_quadrature instead of the normals */
 };
@@ -194,6 +196,13 @@ int rbo_finalize_sums(const double* sums, int d, int ntheta, double* mean, doubl
  *   n_evals[h x m_count] (int32), start_status / start_iters [S x h x m_count] (int32) */
 int rbo_get_tape(rbo_handle* h, double* xs, double* ys, double* gys, double* alphas, int32_t* n_evals,
                  int32_t* start_status, int32_t* start_iters);
+
+/* Extended tape of the last rollout run with RBO_FLAG_TAPE_EX: sx_j = fs(x_j, theta; fantasy_index = j-1) (rbs.jl:482-581), the
+ * surrogate evaluation policy solve j maximised, at the chosen x_j, j = 1..h:
+ *   mu[h x m_count], sigma[h x m_count], dmu[d x h x m_count], dsigma[d x h x m_count], Halpha[d x d x h x m_count] (the
+ *   reference's H alpha, rbs.jl:568, i.e. without the mu-sigma cross term). alphas of rbo_get_tape then holds alpha(x_j) in
+ *   teacher-forced mode as well. Any pointer may be NULL. */
+int rbo_get_tape_ex(rbo_handle* h, double* mu, double* sigma, double* dmu, double* dsigma, double* Halpha);
 
 /* ---- generators the reference's host code provides (utils.jl), same arithmetic on the device -- */
 /* gen_uniform (utils.jl:4-13): dim x npoints Sobol points (Joe-Kuo, Gray code, origin skipped). */

@@ -42,7 +42,8 @@ class Problem(C.Structure):
 class Outputs(C.Structure):
     _fields_ = [("values", _dp), ("grad_x", _dp), ("grad_theta", _dp), ("best_index", _ip), ("grad_case", _ip),
                 ("status", _ip), ("xs", _dp), ("ys", _dp), ("gys", _dp), ("alphas", _dp), ("n_evals", _ip),
-                ("start_status", _ip), ("start_iters", _ip)]
+                ("start_status", _ip), ("start_iters", _ip), ("t_mu", _dp), ("t_sigma", _dp), ("t_dmu", _dp), ("t_dsigma", _dp),
+                ("t_Halpha", _dp)]
 
 
 def build(force=False):
@@ -158,7 +159,10 @@ class OracleProblem:
                      gys=np.zeros((d, h + 1, M), order="F"), alphas=np.zeros((max(h, 1), M), order="F"),
                      n_evals=np.zeros((max(h, 1), M), np.int32, order="F"),
                      start_status=np.zeros((S, max(h, 1), M), np.int32, order="F"),
-                     start_iters=np.zeros((S, max(h, 1), M), np.int32, order="F"))
+                     start_iters=np.zeros((S, max(h, 1), M), np.int32, order="F"),
+                     t_mu=np.zeros((max(h, 1), M), order="F"), t_sigma=np.zeros((max(h, 1), M), order="F"),
+                     t_dmu=np.zeros((d, max(h, 1), M), order="F"), t_dsigma=np.zeros((d, max(h, 1), M), order="F"),
+                     t_Halpha=np.zeros((d, d, max(h, 1), M), order="F"))
         o = Outputs()
         for k, v in r.items():
             setattr(o, k, v.ctypes.data_as(_ip if v.dtype == np.int32 else _dp))

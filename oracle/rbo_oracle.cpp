@@ -315,6 +315,17 @@ void eval_fs(const Ctx& cx, const FS& fs, const double* x, const double* theta, 
   if (level < 2) return;
 
   s.Dw.assign(V.begin() + n, V.end());  // rbs.jl:526  Dw = L'\(L\dkx')
+  if (factored) {
+    // the CUDA kernel's formulation of the mean as well: mu = kx.c = (L^-1 kx).(L^-1 y), grad mu = (L^-1 dkx').(L^-1 y); used by the
+    // 1e-10 step-level comparison (algebraically rbs.jl:513-514, rounded differently by kappa * eps)
+    std::vector<double> u(fs.y.begin(), fs.y.begin() + n);
+    fwd_solve(fs.L.data(), fs.ld, n, u.data(), n, 1);
+    s.mu = dot(Vf.data(), u.data(), n);
+    for (int a = 0; a < d; ++a) s.dmu[a] = dot(Vf.data() + (size_t)(a + 1) * n, u.data(), n);
+    s.g = rule_eval(p->rule_id, p->sigma_tol, s.mu, s.sigma, theta[0], fstar);
+    for (int a = 0; a < d; ++a) s.dal[a] = s.g.g_mu * s.dmu[a] + s.g.g_sig * s.dsig[a];
+    for (int a = 0; a < d; ++a) s.d2a_dxdth[a] = s.dmu[a] * s.g.g_muth + s.dsig[a] * s.g.g_sigth;
+  }
   s.Hmu.assign((size_t)d * d, 0.0); s.Hsig.assign((size_t)d * d, 0.0);
   std::vector<double> Hw((size_t)d * d, 0.0);
   // rbs.jl:516-523, 542-545 with eval_Hk rbf.jl:141-150
@@ -511,10 +522,10 @@ void tri_solve_neg(const double* ta, const double* te, const double* b, int n, d
 // shifts S = {lam >= 0 : T + lam I positive definite and |h(lam)| <= Delta} form a half-line [lam*, inf): lam* = 0 is the
 // interior Newton step (optim.jl:13-21), otherwise the boundary solution, and in the hard case lam* = -lambda_min with
 // |h(lam*)| < Delta, completed along the lowest eigenvector (optim.jl:39-46). lam* is located by TR_ROUNDS rounds of
-// TR_CAND-way multisection (each lane of the CUDA warp tests two candidates), i.e. to 1/(63 * 64^2) = 4e-6 of the initial
+// TR_CAND-way multisection (each lane of the CUDA warp tests two candidates), i.e. to 1/(63 * 64^3) = 6e-8 of the initial
 // bracket: a trust-region step does not need |p| = Delta to more than that. Hff: n x n row-major (overwritten).
 // Returns true when the constraint is active ("hit_constraint").
-constexpr int TR_ROUNDS = 3, TR_CAND = 64;
+constexpr int TR_ROUNDS = 4, TR_CAND = 64;
 bool tr_step(double* Hff, const double* gf, int n, double Delta, double* pout, double* work /* >= 8 n */) {
   double* ta = work; double* te = ta + n; double* beta = te + n; double* gt = beta + 2 * n; double* wk = gt + n;  // wk: 2n
   if (n == 1) {
@@ -1022,6 +1033,14 @@ int orc_rollout(const orc_problem* p, orc_outputs* out) {
             SX sa;
             eval_fs(cx, fs, xnext.data(), p->theta, step - 1, 0, sa);
             out->alphas[(size_t)m * h + (step - 1)] = sa.g.g;
+          }
+          if (out->t_mu) {  // extended tape: sx = fs(x_step, theta; fantasy_index = step - 1) (rbs.jl:482-581)
+            SX sa;
+            eval_fs(cx, fs, xnext.data(), p->theta, step - 1, 2, sa);
+            const size_t o = (size_t)m * h + (step - 1);
+            out->t_mu[o] = sa.mu; out->t_sigma[o] = sa.sigma;
+            for (int a = 0; a < d; ++a) { out->t_dmu[o * d + a] = sa.dmu[a]; out->t_dsigma[o * d + a] = sa.dsig[a]; }
+            for (int i = 0; i < d * d; ++i) out->t_Halpha[o * d * d + i] = sa.Hal_ref[i];
           }
           xloc = xnext.data();
         }

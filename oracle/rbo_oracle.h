@@ -91,6 +91,12 @@ typedef struct {
   int* n_evals;        /* h x M           acquisition evaluations spent at step j (all starts) */
   int* start_status;   /* S x h x M */
   int* start_iters;    /* S x h x M */
+  /* optional extended tape (may be NULL): the surrogate evaluation sx_j = fs(x_j; fantasy_index = j-1) at the chosen x_j */
+  double* t_mu;        /* h x M */
+  double* t_sigma;     /* h x M */
+  double* t_dmu;       /* d x h x M */
+  double* t_dsigma;    /* d x h x M */
+  double* t_Halpha;    /* d x d x h x M   the reference's H alpha (rbs.jl:568, no mu-sigma cross term) */
 } orc_outputs;
 
 void orc_default_solver_opts(orc_solver_opts* o);

@@ -53,6 +53,7 @@ SYMBOLS = {
     "rbo_partial_sums_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "rbo_finalize_sums": (C.c_int, [_dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
     "rbo_get_tape": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _ip, _ip, _ip]),
+    "rbo_get_tape_ex": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp]),
     "rbo_sobol_uniform": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp]),
     "rbo_sobol_uint32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint32)]),
     "rbo_generate_initial_guesses": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]),

@@ -478,11 +478,11 @@ class RolloutEngine:
         self.S = starts.shape[1]
 
     def rollout(self, x0, theta, lbs, ubs, horizon, fmini, values, grad_x=None, grad_theta=None, dual_dirs=None,
-                x_forced=None, best_index=None, grad_case=None, status=None, gauss_hermite=False):
+                x_forced=None, best_index=None, grad_case=None, status=None, gauss_hermite=False, tape_ex=False):
         x0 = np.ascontiguousarray(x0, dtype=np.float64); theta = np.ascontiguousarray(theta, dtype=np.float64)
         lbs = np.ascontiguousarray(lbs, dtype=np.float64); ubs = np.ascontiguousarray(ubs, dtype=np.float64)
         mode = 1 if (grad_x is not None and grad_theta is not None) else 0  # rollout.jl:319
-        flags = (1 if x_forced is not None else 0) | (2 if gauss_hermite else 0)
+        flags = (1 if x_forced is not None else 0) | (2 if gauss_hermite else 0) | (4 if tape_ex else 0)
         if dual_dirs is not None:
             dual_dirs = np.asfortranarray(dual_dirs, dtype=np.float64)
         if x_forced is not None:
@@ -523,6 +523,14 @@ class RolloutEngine:
                  start_iters=np.zeros((S, hh, M), np.int32, order="F"))
         self.handle.check(self.lib.rbo_get_tape(self.handle.h, dptr(r["xs"]), dptr(r["ys"]), dptr(r["gys"]), dptr(r["alphas"]),
                                                 iptr(r["n_evals"]), iptr(r["start_status"]), iptr(r["start_iters"])))
+        return r
+
+    def tape_ex(self, horizon):
+        """Extended tape (rbo_get_tape_ex) of the last rollout run with tape_ex=True."""
+        M, d, hh = self.m_count, self.d, max(horizon, 1)
+        r = dict(mu=np.zeros((hh, M), order="F"), sigma=np.zeros((hh, M), order="F"), dmu=np.zeros((d, hh, M), order="F"),
+                 dsigma=np.zeros((d, hh, M), order="F"), Halpha=np.zeros((d, d, hh, M), order="F"))
+        self.handle.check(self.lib.rbo_get_tape_ex(self.handle.h, dptr(r["mu"]), dptr(r["sigma"]), dptr(r["dmu"]), dptr(r["dsigma"]), dptr(r["Halpha"])))
         return r
 
     def multistart_base_solve(self, theta, lbs, ubs):

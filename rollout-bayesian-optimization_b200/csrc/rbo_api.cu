@@ -78,6 +78,9 @@ struct rbo_handle {
   int vglob_wmax = 0;       // development knob: cap on the start slots of the large-n variant (0 = default)
   int force_vglob = 0;      // development / test knob: use the large-n variant even when shared memory would do
   double* Vscratch = nullptr, *Bscratch = nullptr;
+  double *t_mu = nullptr, *t_sigma = nullptr, *t_dmu = nullptr, *t_dsigma = nullptr, *t_Halpha = nullptr;
+  size_t cap_tex = 0;  // trajectories x steps the extended tape holds
+  bool tex_valid = false;
   // resident surrogate in its canonical device form (rbo_set_surrogate / rbo_condition): L0^-1 row-major with pitch ldi,
   // the observation sites point-major, work vectors
   double *Ld = nullptr, *Linv = nullptr, *Xpts = nullptr, *wk = nullptr;
@@ -179,7 +182,7 @@ int rbo_destroy(rbo_handle* h) {
   cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->Xb, h->yb, h->c0, h->u0, h->Lf, h->Lb, h->Lbf, h->x0_batch, h->rn, h->starts, h->sobol_dirs, h->values, h->grad_x, h->grad_theta, h->xs, h->ys,
                   h->gys, h->alphas, h->best_index, h->grad_case, h->status, h->n_evals, h->start_status, h->start_iters, h->work_counter, h->sums,
-                  h->dual_dirs, h->x_forced, h->cs_tape, h->gh_nodes, h->gh_weights, h->Vscratch, h->Bscratch, h->Ld, h->Linv, h->Xpts, h->wk, h->dstat};
+                  h->dual_dirs, h->x_forced, h->cs_tape, h->gh_nodes, h->gh_weights, h->Vscratch, h->Bscratch, h->Ld, h->Linv, h->Xpts, h->wk, h->dstat, h->t_mu, h->t_sigma, h->t_dmu, h->t_dsigma, h->t_Halpha};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -574,6 +577,18 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   P.status = h->status; P.xs = h->xs; P.ys = h->ys; P.gys = h->gys; P.alphas = h->alphas; P.n_evals = h->n_evals;
   P.start_status = h->tape_enabled ? h->start_status : nullptr; P.start_iters = h->tape_enabled ? h->start_iters : nullptr;
   P.work_counter = h->work_counter;
+  h->tex_valid = false;
+  if (flags & RBO_FLAG_TAPE_EX) {
+    if (myopic) return fail(h, RBO_ERR_ARG, "rbo_rollout: RBO_FLAG_TAPE_EX does not apply to the myopic solve");
+    const size_t n = (size_t)M * std::max(horizon, 1), dd = (size_t)h->d * h->d;
+    if (h->cap_tex < n * dd) {
+      CK(h, dev_realloc(&h->t_mu, n)); CK(h, dev_realloc(&h->t_sigma, n)); CK(h, dev_realloc(&h->t_dmu, n * h->d)); CK(h, dev_realloc(&h->t_dsigma, n * h->d));
+      CK(h, dev_realloc(&h->t_Halpha, n * dd));
+      h->cap_tex = n * dd;
+    }
+    P.t_mu = h->t_mu; P.t_sigma = h->t_sigma; P.t_dmu = h->t_dmu; P.t_dsigma = h->t_dsigma; P.t_Halpha = h->t_Halpha;
+    h->tex_valid = true;
+  }
   const int grid = std::min(M, h->num_sms);
   {
     size_t need = (size_t)grid * (horizon + 2) * pc.NR;
@@ -763,6 +778,20 @@ int rbo_get_tape(rbo_handle* h, double* xs, double* ys, double* gys, double* alp
   if (n_evals) CK(h, cudaMemcpyAsync(n_evals, h->n_evals, M * hh * 4, cudaMemcpyDeviceToHost, h->stream));
   if (start_status) CK(h, cudaMemcpyAsync(start_status, h->start_status, M * hh * S * 4, cudaMemcpyDeviceToHost, h->stream));
   if (start_iters) CK(h, cudaMemcpyAsync(start_iters, h->start_iters, M * hh * S * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return RBO_SUCCESS;
+}
+
+extern "C" int rbo_get_tape_ex(rbo_handle* h, double* mu, double* sigma, double* dmu, double* dsigma, double* Halpha) {
+  if (!h) return RBO_ERR_ARG;
+  if (!h->tex_valid) return fail(h, RBO_ERR_STATE, "rbo_get_tape_ex: the last rollout did not run with RBO_FLAG_TAPE_EX");
+  CK(h, cudaSetDevice(h->device));
+  const size_t n = (size_t)h->outM * std::max(h->outh, 0), d = h->outd;
+  if (mu) CK(h, cudaMemcpyAsync(mu, h->t_mu, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (sigma) CK(h, cudaMemcpyAsync(sigma, h->t_sigma, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (dmu) CK(h, cudaMemcpyAsync(dmu, h->t_dmu, n * d * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (dsigma) CK(h, cudaMemcpyAsync(dsigma, h->t_dsigma, n * d * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (Halpha) CK(h, cudaMemcpyAsync(Halpha, h->t_Halpha, n * d * d * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   return RBO_SUCCESS;
 }

@@ -72,6 +72,7 @@ struct DevProblem {
   int* n_evals;        // [M][h]
   int* start_status;   // [M][h][S]
   int* start_iters;    // [M][h][S]
+  double *t_mu, *t_sigma, *t_dmu, *t_dsigma, *t_Halpha;  // extended tape (RBO_FLAG_TAPE_EX): [M][h], [M][h], [M][h][d], [M][h][d], [M][h][d*d]
   int* work_counter;   // dynamic trajectory scheduler
   double* cs_tape;     // [gridDim.x][h+2][NR] coefficient tape of the trajectory each CTA is working on
   SmemPlan pl;         // make_plan(...) evaluated on the host: the offsets are then constant-bank operands in the kernel

@@ -1079,7 +1079,7 @@ struct K {
   // section 4; modelled on tr_newton, optim.jl:68-114), run by ONE WARP for slot `sl` right after assemble_warp(). Returns
   // true (uniformly) if the slot has a new trial point in sxt and stays active.
   // ------------------------------------------------------------------------------------------------
-  __device__ bool slot_logic_warp(int sl) {
+  __device__ bool slot_logic_warp(int sl, bool single = false) {
     const int d = P.d, dd = d * d;
     const rbo_solver_opts& o = P.so;
     double* x = sm + pl.sx + sl * d; double* xt = sm + pl.sxt + sl * d; double* g = sm + pl.sg + sl * d;
@@ -1128,6 +1128,7 @@ struct K {
       }
       flg = (P.rule_id != RBO_RULE_LCB && at > 0.0) ? 1 : 0;
       accept_state();
+      if (single) return store(RBO_SOLVE_CONVERGED, false);  // one evaluation at a given point (extended tape): no iteration
       double wmax = 0.0;
       for (int a = 0; a < d; ++a) wmax = fmax(wmax, P.ubs[a] - P.lbs[a]);
       Delta = fmin(o.delta0_box * wmax, o.delta0_ell * P.kern.th[0]);
@@ -1219,14 +1220,17 @@ struct K {
   // The coefficients of the active surrogate must be in column CCOL. Result: bestx (argmax), misc[0] = -alpha
   // there, si[I_BEST] (or -1), si[I_EVALS]. Ties resolve to the lowest start index (findmin: first minimum).
   // ------------------------------------------------------------------------------------------------
-  __device__ void multistart(size_t tape_off) {
+  // single = true: ONE evaluation at `bestx` through slot 0 (no clamping, no start list): afterwards slot 0 holds mu, sigma, alpha,
+  // grad mu, grad sigma and the reference's H alpha there (the extended tape of the step-level parity tests).
+  __device__ void multistart(size_t tape_off, bool single = false) {
     const int d = P.d, W = P.W, q1 = d + 1;
     __syncthreads();
     if (tid == 0) {
       si[I_BEST] = -1; si[I_EVALS] = 0; misc[0] = 0.0;
-      const int n0 = min(W, P.S);
+      const int n0 = single ? 1 : min(W, P.S);
       for (int i = 0; i < n0; ++i) { alist[i] = i; load_start(i, i); }
-      si[I_NACT] = n0; si[I_NEXT] = n0;
+      if (single) for (int a = 0; a < d; ++a) (sm + pl.sxt)[a] = bestx[a];
+      si[I_NACT] = n0; si[I_NEXT] = single ? P.S : n0;
     }
     __syncthreads();
     int nact = si[I_NACT];
@@ -1270,7 +1274,7 @@ struct K {
         long long ta_ = clock64();
         if (tid == 0) atomicAdd(&g_phase_cycles[8], (unsigned long long)(ta_ - pt_t0));
 #endif
-        slot_logic_warp(sl);
+        slot_logic_warp(sl, single);
 #ifdef RBO_PHASE_TIMERS
         if (tid == 0) atomicAdd(&g_phase_cycles[14], (unsigned long long)(clock64() - ta_));
 #endif
@@ -1289,8 +1293,8 @@ struct K {
           bool bad = !isfinite(f);
           for (int a = 0; a < d; ++a) bad = bad || isnan(x[a]);
           si[I_EVALS] += sevals[sl];
-          if (P.start_status) P.start_status[tape_off + sid] = sstat[sl];
-          if (P.start_iters) P.start_iters[tape_off + sid] = siter[sl];
+          if (P.start_status && !single) P.start_status[tape_off + sid] = sstat[sl];
+          if (P.start_iters && !single) P.start_iters[tape_off + sid] = siter[sl];
           if (!bad && (si[I_BEST] < 0 || f < misc[0] || (f == misc[0] && sid < si[I_BEST]))) {
             si[I_BEST] = sid; misc[0] = f;
             for (int a = 0; a < d; ++a) bestx[a] = x[a];
@@ -1351,36 +1355,56 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) RBO_KERNEL_NAME(const __grid_c
     k.nf = 0;
     __syncthreads();
 
-    if (P.flags & RBO_FLAG_MYOPIC_INTERNAL) {
-      // multistart_base_solve!(::Surrogate, ...) (rbf_optim.jl:103-134): the base surrogate, no fantasies
-      k.multistart((size_t)m * P.S);
-      if (tid < d) P.xs[(size_t)m * d + tid] = bestx[tid];
-      if (tid == 0) {
-        P.values[m] = -misc[0];
-        if (P.n_evals) P.n_evals[m] = si[I_EVALS];
-        if (P.status) P.status[m] = si[I_TSTATUS];
-        if (P.best_index) P.best_index[m] = si[I_BEST];
-        if (P.grad_case) P.grad_case[m] = 0;
-      }
-      continue;
-    }
-
-    for (int step = 0; step <= h; ++step) {
+    // multistart() is inlined at exactly ONE call site (a second or third copy pushes the kernel over its register budget):
+    // the myopic solve, the policy solves of the rollout and the single evaluation of the extended tape all go through it.
+    const bool myopic = (P.flags & RBO_FLAG_MYOPIC_INTERNAL) != 0;
+    for (int step = myopic ? 1 : 0; step <= (myopic ? 1 : h); ++step) {
       // ============ choose the location x_step ============
       if (step == 0) {
         if (tid < d) bestx[tid] = P.x0_batch ? __ldg(P.x0_batch + (size_t)RBO_MB * d + tid) : P.x0[tid];  // rollout.jl:46
-      } else if (P.flags & RBO_FLAG_TEACHER_FORCED) {
-        if (tid < d) bestx[tid] = P.x_forced[((size_t)RBO_MS * h + (step - 1)) * d + tid];
-        if (tid == 0) { si[I_EVALS] = 0; misc[0] = nan(""); }
+        __syncthreads();
       } else {
-        // multistart_base_solve!(fs, xnext; fantasy_index = step-1) (rollout.jl:58-66, rbf_optim.jl:68-101);
-        // column CCOL holds cs[fantasy_index + 2] (1-based) = the coefficients after `step` fantasies
-        k.multistart(((size_t)m * h + (step - 1)) * P.S);
+        for (int pass = 0; pass < 2; ++pass) {
+          const bool single = pass == 1;  // pass 1: the extended tape's evaluation at the chosen point
+          if (single && (myopic || !(P.flags & RBO_FLAG_TAPE_EX))) break;
+          if (!single && !myopic && (P.flags & RBO_FLAG_TEACHER_FORCED)) {
+            if (tid < d) bestx[tid] = P.x_forced[((size_t)RBO_MS * h + (step - 1)) * d + tid];
+            if (tid == 0) { si[I_EVALS] = 0; misc[0] = nan(""); }
+          } else {
+            // multistart_base_solve!(fs, xnext; fantasy_index = step-1) (rollout.jl:58-66, rbf_optim.jl:68-101) -- column CCOL holds
+            // cs[fantasy_index + 2] (1-based) = the coefficients after `step` fantasies -- or, myopic,
+            // multistart_base_solve!(::Surrogate, ...) (rbf_optim.jl:103-134): the base surrogate, no fantasies
+            if (single) __syncthreads();
+            k.multistart(single ? 0 : (myopic ? (size_t)m * P.S : ((size_t)m * h + (step - 1)) * P.S), single);
+          }
+          __syncthreads();
+          if (!single) {
+            if (!myopic && tid == 0) {
+              if (P.n_evals) P.n_evals[(size_t)m * h + step - 1] = si[I_EVALS];
+              if (P.alphas) P.alphas[(size_t)m * h + step - 1] = -misc[0];
+            }
+          } else {
+            // extended tape: sx = fs(x_step, theta; fantasy_index = step - 1), the surrogate evaluation the
+            // policy solve of this step maximised (rbs.jl:482-581); slot 0 holds it after the single evaluation
+            const size_t o = (size_t)m * h + step - 1;
+            const double* gh = smem + k.pl.sgh;
+            if (tid == 0) { P.t_mu[o] = gh[6]; P.t_sigma[o] = gh[5]; if (P.alphas) P.alphas[o] = gh[0]; }
+            for (int i = tid; i < d; i += RBO_THREADS) { P.t_dmu[o * d + i] = (smem + k.pl.sdmu)[i]; P.t_dsigma[o * d + i] = (smem + k.pl.sdsig)[i]; }
+            for (int i = tid; i < d * d; i += RBO_THREADS) P.t_Halpha[o * d * d + i] = (smem + k.pl.sHref)[i];
+            __syncthreads();
+          }
+        }
       }
-      __syncthreads();
-      if (step > 0 && tid == 0) {
-        if (P.n_evals) P.n_evals[(size_t)m * h + step - 1] = si[I_EVALS];
-        if (P.alphas) P.alphas[(size_t)m * h + step - 1] = -misc[0];
+      if (myopic) {
+        if (tid < d) P.xs[(size_t)m * d + tid] = bestx[tid];
+        if (tid == 0) {
+          P.values[m] = -misc[0];
+          if (P.n_evals) P.n_evals[m] = si[I_EVALS];
+          if (P.status) P.status[m] = si[I_TSTATUS];
+          if (P.best_index) P.best_index[m] = si[I_BEST];
+          if (P.grad_case) P.grad_case[m] = 0;
+        }
+        break;
       }
 
       // ============ joint draw at x_step (observables.jl:106-121, rbs.jl:588-611) and condition! (rbs.jl:431-441) ============
@@ -1486,6 +1510,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) RBO_KERNEL_NAME(const __grid_c
       }
     }
 
+    if (myopic) continue;
     // ============ resolve (rollout.jl:108-111) and bookkeeping ============
     if (tid == 0) {
       double best = k.yf[0];

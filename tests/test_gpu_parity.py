@@ -723,3 +723,40 @@ def test_failed_trajectories_poison_the_device_resident_estimate(pkg, orc):
         assert eng.lib.rbo_finalize_sums(p(host), d, 1, C.byref(m), None, None, None, None, None) == -5
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("name,kw", [("C2", dict(M=32, S=6)), ("GP:2:0.25", dict(M=32, N=12, h=3)), ("C3", dict(M=16, N=64, h=3))])
+def test_extended_tape_step_level_parity(pkg, orc, name, kw):
+    """teacher-forced (identical x_j on both sides), EVERY quantity of the surrogate evaluation the policy
+    solve maximised -- mu, sigma, grad mu, grad sigma, alpha and the reference's H alpha (rbs.jl:568, no cross term) at each x_j,
+    j = 1..h -- entry-wise, relative to the largest entry of the quantity: 1e-10 against the oracle evaluating the REFERENCE's forms
+    (mu = kx.c, sigma^2 = k0 - kx.(K^-1 kx) with two triangular solves; observed 1e-15..1e-13 on every step: the kernel's products
+    with the correctly rounded explicit inverse are as accurate as the substitutions). The oracle's own forward-solve variant
+    (ORC_FLAG_FACTORED: mu = (L^-1 kx).(L^-1 y) by substitution) is the LESS accurate of the three and is only held to 1e-8."""
+    wl, sur, rn, starts, dd = setup(pkg, orc, name, **kw)
+    free = oracle_problem(orc, wl, sur, rn, starts, 1, dual_dirs=dd).rollout()
+    xf = np.asfortranarray(free["xs"][:, 1:, :])
+    eng = pkg.RolloutEngine(0)
+    try:
+        eng.set_surrogate(pkg.FantasySurrogate(sur, wl.h)); eng.set_normals(rn); eng.set_starts(starts)
+        v, gx, gt = np.zeros(wl.M), np.zeros((wl.d, wl.M), order="F"), np.zeros((1, wl.M), order="F")
+        eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), v, gx, gt, dual_dirs=dd, x_forced=xf, tape_ex=True)
+        tape, tex = eng.tape(wl.h), eng.tape_ex(wl.h)
+    finally:
+        eng.close()
+    N_ = sur.observed
+    kappa = max(np.linalg.cond(pkg.eval_KXX(sur.ψ, np.concatenate([sur.X[:, :N_], free["xs"][:, :, m]], axis=1), sur.σn2)) for m in range(wl.M))
+    report = {}
+    for flags, tol in ((0, 1e-10), (orc.FLAG_FACTORED, 1e-8)):
+        ref = oracle_problem(orc, wl, sur, rn, starts, 1, dual_dirs=dd, x_forced=xf, flags=flags).rollout()
+        scale = lambda a: max(np.abs(a).max(), 1e-300)
+        for key, got in (("t_mu", tex["mu"]), ("t_sigma", tex["sigma"]), ("t_dmu", tex["dmu"]), ("t_dsigma", tex["dsigma"]), ("t_Halpha", tex["Halpha"]),
+                         ("alphas", tape["alphas"])):
+            hax = got.ndim - 2  # the step axis
+            first = np.abs(np.take(got, 0, axis=hax) - np.take(ref[key], 0, axis=hax)).max() / scale(ref[key])
+            err = np.abs(got - ref[key]).max() / scale(ref[key])
+            report[(key, flags)] = (first, err)
+            assert err < tol, (key, flags, first, err, kappa)
+        assert relerr(tape["ys"], ref["ys"]) < 1e-9 and relerr(v, ref["values"]) < 1e-9
+    print(f"extended tape {name}: kappa_ext = {kappa:.2e}; (step 1, all steps) errors " +
+          ", ".join(f"{k[0]}{'(factored oracle)' if k[1] else ''}=({e[0]:.1e}, {e[1]:.1e})" for k, e in report.items()))
