@@ -43,6 +43,10 @@ enum {
   RBO_FLAG_TEACHER_FORCED = 1, /* x_1..x_h supplied by the caller (step-level parity tests) */
   RBO_FLAG_TAPE_EX = 4,        /* also record mu, sigma, grad mu, grad sigma, H alpha, alpha of the policy solve's surrogate evaluation at
                                   every chosen x_j (one extra evaluation per step): rbo_get_tape_ex */
+  RBO_FLAG_REPLAY_TAPE = 8,    /* teacher-force the x-path the PREVIOUS rollout of this handle left on the device (same samples, same horizon):
+                                  second phase of the two-phase call that reproduces the reference's rand(dim) consumption (rollout.jl:133):
+                                  phase 1 = RBO_MODE_VALUE (values, best_index), host draws the dual directions for the case-3 samples
+                                  in the reference's order, phase 2 = RBO_MODE_VALUE_GRAD | this flag (no inner solves, bitwise replay) */
   RBO_FLAG_GAUSS_HERMITE = 2   /* simulate_trajectory_ghq (rollout.jl:409-467): GaussHermiteObservable draws (observables.jl:32-81,157)
                                   from the nodes / weights of rbo_set_quadrature instead of the normals */
 };

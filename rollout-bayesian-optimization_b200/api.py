@@ -478,11 +478,14 @@ class RolloutEngine:
         self.S = starts.shape[1]
 
     def rollout(self, x0, theta, lbs, ubs, horizon, fmini, values, grad_x=None, grad_theta=None, dual_dirs=None,
-                x_forced=None, best_index=None, grad_case=None, status=None, gauss_hermite=False, tape_ex=False):
+                x_forced=None, best_index=None, grad_case=None, status=None, gauss_hermite=False, tape_ex=False, replay=False,
+                want_grad=None):
         x0 = np.ascontiguousarray(x0, dtype=np.float64); theta = np.ascontiguousarray(theta, dtype=np.float64)
         lbs = np.ascontiguousarray(lbs, dtype=np.float64); ubs = np.ascontiguousarray(ubs, dtype=np.float64)
         mode = 1 if (grad_x is not None and grad_theta is not None) else 0  # rollout.jl:319
-        flags = (1 if x_forced is not None else 0) | (2 if gauss_hermite else 0) | (4 if tape_ex else 0)
+        if want_grad is not None:
+            mode = 1 if want_grad else 0
+        flags = (1 if x_forced is not None else 0) | (2 if gauss_hermite else 0) | (4 if tape_ex else 0) | (8 if replay else 0)
         if dual_dirs is not None:
             dual_dirs = np.asfortranarray(dual_dirs, dtype=np.float64)
         if x_forced is not None:
@@ -559,13 +562,28 @@ def _mean_std_rows(A):
     return mu, sd
 
 
+def draw_dual_directions(values, best_index, d, h, rand=np.random.rand):
+    """The rand(dim) draws of solve_dual_y (rollout.jl:133) in the reference's consumption order: samples in ascending order; only
+    those whose gradient is the back-substitution of rollout.jl:253-276 (payoff > 0 and best step t >= 1); for each, j = t, t-1,
+    .., 1 fills the direction of solve_index j-1. Returns d x h x M (zeros where the reference draws nothing)."""
+    M = len(values)
+    dd = np.zeros((d, max(h, 1), M), order="F")
+    for m in range(M):
+        t = int(best_index[m])
+        if values[m] > 0.0 and t >= 1:       # case 3: fmini > best observation and the best step is a fantasy step
+            for j in range(t, 0, -1):
+                dd[:, j - 1, m] = rand(d)
+    return dd
+
+
 def simulate_trajectory_mc(T, tp, *, inner_solve_xstarts, resolutions, spatial_gradients_container=None,
-                           hyperparameter_gradients_container=None, dual_directions=None, device=0, keep_resident=False):
+                           hyperparameter_gradients_container=None, dual_directions=None, device=0, keep_resident=False, rng_rand=None):
     """simulate_trajectory_mc (rollout.jl:279-340) on the GPU.
 
     Fills `resolutions[m]` and the gradient containers in place and returns ExpectedTrajectoryOutput, exactly
     like the reference. `dual_directions` (d x h x M) stands for the `rand(dim)` draws of rollout.jl:133 (Q5); by
-    default they are drawn from numpy's global RNG, as the reference draws them from Julia's.
+    default they are drawn from the host RNG (`rng_rand`, default numpy's global one) in the reference's own
+    data-dependent consumption order through a two-phase call (see draw_dual_directions).
     Raises RboError if a trajectory failed where the reference would have thrown (first failing sample).
     """
     d, h, M = len(tp.x0), tp.horizon, tp.mc_iters
@@ -577,14 +595,23 @@ def simulate_trajectory_mc(T, tp, *, inner_solve_xstarts, resolutions, spatial_g
             eng.set_normals(tp.rnstream_sequence)
             eng.set_starts(inner_solve_xstarts)
         want_grad = spatial_gradients_container is not None and hyperparameter_gradients_container is not None
-        if want_grad and dual_directions is None and h > 0:
-            dual_directions = np.asfortranarray(np.random.rand(d, h, M))
         fmini = float(np.min(get_observations(T.s)))  # rollout.jl:109 (zero-padded capacity vector, Q2)
         status = np.zeros(M, np.int32)
-        summary = eng.rollout(tp.x0, tp.θ, tp.spatial_lbs, tp.spatial_ubs, h, fmini, resolutions,
-                              spatial_gradients_container if want_grad else None,
-                              hyperparameter_gradients_container if want_grad else None,
-                              dual_dirs=dual_directions if want_grad else None, status=status)
+        if want_grad and dual_directions is None and h > 0:
+            # Two-phase call (rollout.jl:133, Q5): the reference draws rand(dim) inside solve_dual_y, i.e. only for the trajectories
+            # whose gradient takes the back-substitution (case 3), t draws each (j = t, t-1, .., 1 -> solve_index j-1), in sample
+            # order. Phase 1 computes values and best indices, the host replays exactly that consumption of its global RNG,
+            # phase 2 replays the device-resident x-path (bitwise, no inner solves) with the gradient.
+            best = np.zeros(M, np.int32)
+            eng.rollout(tp.x0, tp.θ, tp.spatial_lbs, tp.spatial_ubs, h, fmini, resolutions, best_index=best, status=status, want_grad=False)
+            dual_directions = draw_dual_directions(resolutions, best, d, h, rand=rng_rand if rng_rand is not None else np.random.rand)
+            summary = eng.rollout(tp.x0, tp.θ, tp.spatial_lbs, tp.spatial_ubs, h, fmini, resolutions, spatial_gradients_container,
+                                  hyperparameter_gradients_container, dual_dirs=dual_directions, status=status, replay=True)
+        else:
+            summary = eng.rollout(tp.x0, tp.θ, tp.spatial_lbs, tp.spatial_ubs, h, fmini, resolutions,
+                                  spatial_gradients_container if want_grad else None,
+                                  hyperparameter_gradients_container if want_grad else None,
+                                  dual_dirs=dual_directions if want_grad else None, status=status)
     finally:
         if keep_resident:
             T._engine = eng

@@ -81,6 +81,7 @@ struct rbo_handle {
   double *t_mu = nullptr, *t_sigma = nullptr, *t_dmu = nullptr, *t_dsigma = nullptr, *t_Halpha = nullptr;
   size_t cap_tex = 0;  // trajectories x steps the extended tape holds
   bool tex_valid = false;
+  bool xs_valid = false;  // the x-path of the last rollout is on the device (RBO_FLAG_REPLAY_TAPE)
   // resident surrogate in its canonical device form (rbo_set_surrogate / rbo_condition): L0^-1 row-major with pitch ldi,
   // the observation sites point-major, work vectors
   double *Ld = nullptr, *Linv = nullptr, *Xpts = nullptr, *wk = nullptr;
@@ -465,7 +466,7 @@ int rbo_set_starts(rbo_handle* h, const double* starts, int S) {
 static int ensure_outputs(rbo_handle* h, int M, int hor, int S, int d, int nth) {
   if (h->outM == M && h->outh == hor && h->outS == S && h->outd == d && h->outnth == nth) return RBO_SUCCESS;
   const int hh = std::max(hor, 1);
-  h->outM = 0; h->outh = -1;  // the cache key is only valid once every buffer below exists
+  h->outM = 0; h->outh = -1; h->xs_valid = false;  // the cache key is only valid once every buffer below exists
   CK(h, dev_realloc(&h->values, (size_t)M));
   CK(h, dev_realloc(&h->grad_x, (size_t)M * d));
   CK(h, dev_realloc(&h->grad_theta, (size_t)M * nth));
@@ -547,7 +548,11 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   if (ghq && horizon + 1 > h->gh_depth) return fail(h, RBO_ERR_ARG, "rbo_rollout: quadrature depth %d < horizon + 1 = %d", h->gh_depth, horizon + 1);
   const int Ms = myopic ? 1 : (ghq ? h->gh_M : h->M);  // sample indices
   const int M = Ms * std::max(B, 1);                    // trajectories of this launch
-  if ((flags & RBO_FLAG_TEACHER_FORCED) && !x_forced_dev) return fail(h, RBO_ERR_ARG, "rbo_rollout: teacher forcing without x_forced");
+  if (flags & RBO_FLAG_REPLAY_TAPE) {
+    // second phase of the two-phase call: replay the x-path of the previous rollout of this handle (still on the device)
+    if (myopic || h->outh != horizon || h->outM != M || !h->xs_valid) return fail(h, RBO_ERR_STATE, "rbo_rollout: RBO_FLAG_REPLAY_TAPE needs a preceding rollout with the same samples and horizon on this handle");
+    flags |= RBO_FLAG_TEACHER_FORCED;
+  } else if ((flags & RBO_FLAG_TEACHER_FORCED) && !x_forced_dev) return fail(h, RBO_ERR_ARG, "rbo_rollout: teacher forcing without x_forced");
   if (mode != RBO_MODE_VALUE && mode != RBO_MODE_VALUE_GRAD) return fail(h, RBO_ERR_ARG, "rbo_rollout: bad mode");
   for (int a = 0; a < h->d; ++a)
     if (!(lbs[a] <= ubs[a])) return fail(h, RBO_ERR_ARG, "rbo_rollout: lower bound above upper bound in dimension %d", a);
@@ -612,6 +617,7 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(h->ev1, h->stream));
   h->last_h = horizon; h->last_mode = mode; h->last_nth = ntheta;
+  h->xs_valid = !myopic;
   if (want_summary && summary) {
     std::vector<double> sums(h->sums_len);
     int wd[16] = {0};
@@ -682,11 +688,11 @@ int rbo_rollout(rbo_handle* h, const double* x0, const double* theta, int ntheta
   const size_t nd = Mrun * std::max(horizon, 0) * h->d;
   int rc = upload_opt(h, (mode == RBO_MODE_VALUE_GRAD) ? dual_dirs : nullptr, nd, &h->dual_dirs, &h->dual_cap);
   if (rc) return rc;
-  rc = upload_opt(h, (flags & RBO_FLAG_TEACHER_FORCED) ? x_forced : nullptr, nd, &h->x_forced, &h->forced_cap);
+  rc = upload_opt(h, ((flags & RBO_FLAG_TEACHER_FORCED) && !(flags & RBO_FLAG_REPLAY_TAPE)) ? x_forced : nullptr, nd, &h->x_forced, &h->forced_cap);
   if (rc) return rc;
   rbo_summary local;
   rc = launch_rollout(h, x0, theta, ntheta, lbs, ubs, horizon, fmini, mode, flags, (mode == RBO_MODE_VALUE_GRAD && dual_dirs) ? h->dual_dirs : nullptr,
-                      (flags & RBO_FLAG_TEACHER_FORCED) ? h->x_forced : nullptr, true, summary ? summary : &local);
+                      ((flags & RBO_FLAG_TEACHER_FORCED) && !(flags & RBO_FLAG_REPLAY_TAPE)) ? h->x_forced : nullptr, true, summary ? summary : &local);
   if (rc) return rc;
   const size_t M = Mrun;
   CK(h, cudaMemcpyAsync(values, h->values, M * 8, cudaMemcpyDeviceToHost, h->stream));

@@ -7,8 +7,8 @@ namespace rbo {
 // Shared-memory plan (offsets in doubles from the start of dynamic shared memory).
 struct SmemPlan {
   int V, Fp, G, u, Xf, yf, gyf, Xs, stage, mbar;
-  int sx, sxt, sg, sH, sA, sp;               // per slot: x, trial x, gradient, Hessian, Cholesky scratch, step
-  int sHt, sHref, sga, sdmu, sdsig, sgh;     // per slot: trial Hessian (-H alpha), reference H alpha, grad alpha, grad mu, grad sigma, scalars
+  int sx, sxt, sg, sH, sp;                   // per slot: x, trial x, gradient, Hessian of the merit
+  int sHt, sHref, sga, sdmu, sdsig, sgh;     // per slot: trial Hessian (also the trust-region scratch), grad alpha, grad mu, grad sigma, scalars; sHref: ONE d x d reference H alpha
   int sf, slam, spred, shs, ssn;             // per slot scalars: merit f, trust-region radius, predicted decrease, alpha, |step|_2
   int ppre, ppost, phess;                    // partial sums of the row reductions
   int bestx, misc, adj;                      // [d] best candidate ; scalar/scratch area ; adjoint duals
@@ -99,8 +99,8 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.Xs = take(xsm ? d * (N8 + 1) : 0);
   p.stage = take(RBO_NSTAGE * RBO_CHUNK_K * RBO_LP);
   p.mbar = take(2 * RBO_NSTAGE + 2);
-  p.sx = take(W * d); p.sxt = take(W * d); p.sg = take(W * d); p.sH = take(W * dd); p.sA = take(W * dd); p.sp = take(2);
-  p.sHt = take(W * dd); p.sHref = take(W * dd); p.sga = take(W * d); p.sdmu = take(W * d); p.sdsig = take(W * d); p.sgh = take(W * 8);
+  p.sx = take(W * d); p.sxt = take(W * d); p.sg = take(W * d); p.sH = take(W * dd); p.sp = take(2);
+  p.sHt = take(W * dd); p.sHref = take(dd); p.sga = take(W * d); p.sdmu = take(W * d); p.sdsig = take(W * d); p.sgh = take(W * 8);
   p.sf = take(W); p.slam = take(W); p.spred = take(W); p.shs = take(W); p.ssn = take(W);
   p.ppre = take(RSmax * W * q1);
   p.ppost = take(RSmax * NPmax);

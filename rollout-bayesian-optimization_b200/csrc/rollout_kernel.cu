@@ -829,12 +829,12 @@ struct K {
   // ------------------------------------------------------------------------------------------------
   // s2/tq come from `p1` (q1 outputs per point: |v0|^2, V_p.v0), the Gram V_p.V_q from `pg` (d x d per point).
   __device__ void assemble_warp(int sl, int aidx, int np, int RSpre, const double* p1, int nout1, int RS1, const double* pg, int noutg, int goff, int gld,
-                                int RSg, int RShc, int RShw, double fstar) {
+                                int RSg, int RShc, int RShw, double fstar, double* Href /* d x d or nullptr: the reference's H alpha is only kept for the adjoint / extended tape */) {
     const int d = P.d, dd = d * d, q1 = d + 1, T2 = d * (d + 1) / 2;
     const double* ppre = sm + pl.ppre; const double* phess = sm + pl.phess;
     const int nout_pre = np * q1;
     double* dmu = sm + pl.sdmu + sl * d; double* dsig = sm + pl.sdsig + sl * d; double* ga = sm + pl.sga + sl * d;
-    double* Ht = sm + pl.sHt + sl * dd; double* Href = sm + pl.sHref + sl * dd; double* gh = sm + pl.sgh + sl * 8;
+    double* Ht = sm + pl.sHt + sl * dd; double* gh = sm + pl.sgh + sl * 8;
     auto pre = [&](int e) {
       double s = 0.0;
       if (RSpre < 0) { for (int r = 0; r < RS1; ++r) s += p1[(size_t)r * nout1 + e * (-RSpre) + q1]; }  // V_e . u from the fused product
@@ -864,7 +864,7 @@ struct K {
       double hs = (-dsig[p] * dsig[q] - gram - hw) * isg;                                                            // rbs.jl:541-546
       double href = g.g_mumu * dmu[p] * dmu[q] + g.g_mu * hc + g.g_sigsig * dsig[p] * dsig[q] + g.g_sig * hs;        // rbs.jl:568
       double htrue = href + g.g_musig * (dmu[p] * dsig[q] + dsig[p] * dmu[q]);
-      Href[p * d + q] = href; Href[q * d + p] = href;
+      if (Href) { Href[p * d + q] = href; Href[q * d + p] = href; }
       Ht[p * d + q] = -htrue; Ht[q * d + p] = -htrue;
       fin = fin && isfinite(htrue);
     }
@@ -1083,8 +1083,10 @@ struct K {
     const int d = P.d, dd = d * d;
     const rbo_solver_opts& o = P.so;
     double* x = sm + pl.sx + sl * d; double* xt = sm + pl.sxt + sl * d; double* g = sm + pl.sg + sl * d;
-    double* H = sm + pl.sH + sl * dd; double* A = sm + pl.sA + sl * dd;
-    const double* Ht = sm + pl.sHt + sl * dd; const double* ga = sm + pl.sga + sl * d; const double* gh = sm + pl.sgh + sl * 8;
+    double* H = sm + pl.sH + sl * dd;
+    double* Ht = sm + pl.sHt + sl * dd;  // trial Hessian from the evaluation; dead after the accept decision, then the scratch of the trust-region step
+    double* A = Ht;
+    const double* ga = sm + pl.sga + sl * d; const double* gh = sm + pl.sgh + sl * 8;
     int* fr = sfr + 32 * sl;
     // per-slot scalars: merit f, trust-region radius, predicted decrease of the pending trial, alpha at x
     double f = (sm + pl.sf)[sl], Delta = (sm + pl.slam)[sl], pred = (sm + pl.spred)[sl], alpha = (sm + pl.shs)[sl];
@@ -1269,7 +1271,7 @@ struct K {
       // per-start logic: one warp per active slot
       for (int s = warp; s < nact; s += RBO_NWARPS) {
         const int sl = alist[s];
-        assemble_warp(sl, s, nact, -q2, sm + pl.ppost + s * q1 * q2, nact * q1 * q2, RS1, sm + pl.ppost, nact * q1 * q2, s * q1 * q2 + q2 + 1, q2, RSg, RShc, RShw, misc[1]);
+        assemble_warp(sl, s, nact, -q2, sm + pl.ppost + s * q1 * q2, nact * q1 * q2, RS1, sm + pl.ppost, nact * q1 * q2, s * q1 * q2 + q2 + 1, q2, RSg, RShc, RShw, misc[1], single ? sm + pl.sHref : nullptr);
 #ifdef RBO_PHASE_TIMERS
         long long ta_ = clock64();
         if (tid == 0) atomicAdd(&g_phase_cycles[8], (unsigned long long)(ta_ - pt_t0));
@@ -1368,7 +1370,8 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) RBO_KERNEL_NAME(const __grid_c
           const bool single = pass == 1;  // pass 1: the extended tape's evaluation at the chosen point
           if (single && (myopic || !(P.flags & RBO_FLAG_TAPE_EX))) break;
           if (!single && !myopic && (P.flags & RBO_FLAG_TEACHER_FORCED)) {
-            if (tid < d) bestx[tid] = P.x_forced[((size_t)RBO_MS * h + (step - 1)) * d + tid];
+            // teacher forcing: the caller's x-path, or (RBO_FLAG_REPLAY_TAPE) the x-path the previous rollout left on the device
+            if (tid < d) bestx[tid] = (P.flags & RBO_FLAG_REPLAY_TAPE) ? P.xs[((size_t)m * (h + 1) + step) * d + tid] : P.x_forced[((size_t)RBO_MS * h + (step - 1)) * d + tid];
             if (tid == 0) { si[I_EVALS] = 0; misc[0] = nan(""); }
           } else {
             // multistart_base_solve!(fs, xnext; fantasy_index = step-1) (rollout.jl:58-66, rbf_optim.jl:68-101) -- column CCOL holds
@@ -1593,11 +1596,11 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) RBO_KERNEL_NAME(const __grid_c
           if (k.warp == 0) {
             double fst = P.ymin_base;  // f* over the active slice y[1:N+i]
             for (int j = 0; j < i; ++j) fst = fmin(fst, k.yf[j]);
-            k.assemble_warp(0, 0, 1, RSpre, smem + k.pl.ppost, q1 * q1, RSpost, smem + k.pl.ppost, q1 * q1, q1 + 1, q1, RSpost, RShess, RShess, fst);
+            k.assemble_warp(0, 0, 1, RSpre, smem + k.pl.ppost, q1 * q1, RSpost, smem + k.pl.ppost, q1 * q1, q1 + 1, q1, RSpost, RShess, RShess, fst, smem + k.pl.sHref);
             if (tid == 0) {
               misc[2] = fst;
               // ---- solve_dual_x for j = i (rollout.jl:150-191) with the contributions of later solves already pushed ----
-              double* Hlu = smem + k.pl.sA;  // slot-0 scratch (d x d)
+              double* Hlu = smem + k.pl.sHt;  // slot-0 scratch (d x d): the trial Hessian is not needed here
               const double* Href = smem + k.pl.sHref;
               int piv[RBO_MAXD];
               double det;

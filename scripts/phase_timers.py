@@ -6,8 +6,8 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import __graft_entry__ as g
 
-NAMES = ["fill_columns", "reduce_pre", "fwd_solve", "reduce_post", "bwd_solve", "reduce_hess", "slot_logic", "bookkeeping",
-         "  logic:assemble(w0)", "round_gap", "draw+condition", "adjoint", "wait_full(fwd,w0)", "wait_full(bwd,w0)", "  logic:solver(w0)", "rounds"]
+NAMES = ["fill_columns", "reduce_pre", "fwd_solve", "reduce_post", "bwd_solve", "reduce_hess", "logic team: solver steps (shared-memory build: overlapped)", "compute team waits for logic",
+         "logic team: assemble", "logic team waits for compute", "draw+condition", "adjoint", "wait_full(fwd,w0)", "wait_full(bwd,w0)", "  logic:solver(w0) [large-n build]", "rounds"]
 
 def main(name="C3", M=296, large_n=False):
     pkg = g.load_package()
@@ -38,7 +38,7 @@ def main(name="C3", M=296, large_n=False):
     print(f"{name} M={M}: kernel_ms={s.kernel_ms:.2f} traj/s={M / s.kernel_ms * 1e3:.1f} rounds/traj={rounds / M:.1f} evals/traj={s.n_evals / M:.1f} cycles/traj={tot / M:.3e}")
     for i in range(15):
         if NAMES[i] != "-":
-            print(f"  {NAMES[i]:<16} {100 * out[i] / tot:5.1f}%   {out[i] / max(rounds, 1):9.0f} cycles/round")
+            print(f"  {NAMES[i]:<60} {100 * out[i] / tot:5.1f}%   {out[i] / max(rounds, 1):9.0f} cycles/round")
     fa(eng.handle.h, aux, 0)
     AN = ["setup", "fan-pre", "chunk loop", "  mma+store", "  diag sync+store", "-", "calls(x cycles~1)", "-"]
     for half, nm in ((0, "fwd"), (8, "bwd")):

@@ -760,3 +760,34 @@ def test_extended_tape_step_level_parity(pkg, orc, name, kw):
         assert relerr(tape["ys"], ref["ys"]) < 1e-9 and relerr(v, ref["values"]) < 1e-9
     print(f"extended tape {name}: kappa_ext = {kappa:.2e}; (step 1, all steps) errors " +
           ", ".join(f"{k[0]}{'(factored oracle)' if k[1] else ''}=({e[0]:.1e}, {e[1]:.1e})" for k, e in report.items()))
+
+
+def test_two_phase_call_reproduces_the_reference_rng_consumption(pkg, orc):
+    """rollout.jl:133 draws rand(dim) inside solve_dual_y: only for case-3 trajectories, t draws each (j = t .. 1), in sample order.
+    simulate_trajectory_mc reproduces that consumption with a two-phase call (values first, then a bitwise replay of the
+    device-resident x-path with the gradient). Emulated here with ONE numpy stream on both sides: the oracle is run in two phases
+    the same way (forward, serial draw, teacher-forced gradient); case-3 gradients must then agree."""
+    wl, sur, rn, starts, _ = setup(pkg, orc, "GP:2:0.25", M=64, N=12, h=3)
+    fs = pkg.FantasySurrogate(sur, wl.h)
+    T = pkg.Trajectory(sur, fs, start=wl.x0, hypers=wl.theta, horizon=wl.h)
+    tp = pkg.TrajectoryParameters(wl.x0, wl.theta, wl.h, wl.M, True, wl.lbs, wl.ubs, rnstream_sequence=rn)
+    res, gx, gt = np.zeros(wl.M), np.zeros((wl.d, wl.M), order="F"), np.zeros((1, wl.M), order="F")
+    rs = np.random.RandomState(1906)
+    eto = pkg.simulate_trajectory_mc(T, tp, inner_solve_xstarts=starts, resolutions=res, spatial_gradients_container=gx,
+                                     hyperparameter_gradients_container=gt, rng_rand=rs.rand)
+    after = rs.rand()
+    # the oracle, two-phase, with its own copy of the same stream
+    fwd = oracle_problem(orc, wl, sur, rn, starts, 0).rollout()
+    rs2 = np.random.RandomState(1906)
+    dd = pkg.draw_dual_directions(fwd["values"], fwd["best_index"], wl.d, wl.h, rand=rs2.rand)
+    assert rs2.rand() == after                                # the same number of draws left the stream
+    sel = (fwd["values"] > 0) & (fwd["best_index"] >= 1)
+    assert sel.sum() >= 8 and np.count_nonzero(dd.any(axis=0)) == int(fwd["best_index"][sel].sum())
+    ref = oracle_problem(orc, wl, sur, rn, starts, 1, dual_dirs=dd, x_forced=np.asfortranarray(fwd["xs"][:, 1:, :])).rollout()
+    assert relerr(res, ref["values"]) < 1e-8
+    c3 = ref["grad_case"] == 3
+    assert c3.sum() == sel.sum()
+    gscale = np.maximum(np.abs(ref["grad_x"]).max(axis=0, keepdims=True), 1e-6)
+    err = np.max(np.abs(gx - ref["grad_x"]) / gscale, axis=0)
+    assert np.mean(err[c3] < 1e-6) >= 0.97 and np.all(err[~c3] < 1e-6), np.sort(err)[-4:]
+    assert np.isclose(pkg.mean(eto), res.mean())
