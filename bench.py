@@ -394,7 +394,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
                 "steps": e2e_steps, "all_trajectories_ok": ok_e2e, "host_breakdown_ms": brk},
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": 3 * args.steps,  # rollout kernel + statistics + partial-sums gather per step
         "roofline": {"bound": "tensor", "pipe": "FP64 (mma.sync.m8n8k4.f64 and DFMA share the same 64 FMA/clk/SM)", "achieved": achieved_per_gpu, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_per_gpu / peak_tf,
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload (1 GPU), from the ncu
                      # capture named in traffic_source

@@ -75,6 +75,7 @@ struct rbo_handle {
   int last_h = 0, last_mode = 0, last_nth = 1;
   bool tape_enabled = true;
   double htol = 1e-4;
+  int rs_cap = 0;           // development knob: cap on the row splits of the Gram reductions (0 = default)
   int vglob_wmax = 0;       // development knob: cap on the start slots of the large-n variant (0 = default)
   int force_vglob = 0;      // development / test knob: use the large-n variant even when shared memory would do
   double* Vscratch = nullptr, *Bscratch = nullptr;
@@ -211,6 +212,7 @@ int rbo_set_tuning(rbo_handle* h, int key, int value) {
   switch (key) {
     case RBO_TUNE_LARGE_N: h->force_vglob = value != 0; return RBO_SUCCESS;
     case RBO_TUNE_LARGE_N_SLOTS: if (value < 0 || value > RBO_NCONS) break; h->vglob_wmax = value; return RBO_SUCCESS;
+    case 4: if (value < 0 || value > 4) break; h->rs_cap = value; return RBO_SUCCESS;  // undocumented: row-split cap (plan experiments)
     default: break;
   }
   return fail(h, RBO_ERR_ARG, "rbo_set_tuning: unknown key %d or value %d out of range", key, value);
@@ -511,7 +513,7 @@ static bool choose_plan(const rbo_handle* h, int hor, int S, int mode, PlanChoic
   };
   const int Wmax = std::min(S, RBO_NCONS);
   for (int W = Wmax; !h->force_vglob && W >= std::max(1, std::min(Wmax, (S + 1) / 2)); --W) {
-    int rs = std::min(4, std::max(2, RBO_NWARPS / W));
+    int rs = std::min(h->rs_cap > 0 ? h->rs_cap : 4, std::min(4, std::max(2, RBO_NWARPS / W)));
     if (try_plan(W, rs, 1)) return true;
     if (rs > 2 && try_plan(W, 2, 1)) return true;
   }
@@ -522,7 +524,9 @@ static bool choose_plan(const rbo_handle* h, int hor, int S, int mode, PlanChoic
   // Large-n variant (north_star: "L0 ... read through L2 when n is large"; BASELINE config C5): the work matrix moves to a
   // per-CTA scratch in global memory (it stays L2-resident), everything else keeps its place in shared memory. The base
   // locations are then read through L1 as well. More start slots per round amortise the stream of L0^-1 over more columns.
-  const int Wg = std::min(Wmax, h->vglob_wmax > 0 ? h->vglob_wmax : 8);
+  // measured at the C5 shape (n = 1000, d = 20): 4-5 slots are best; more slots enlarge the scratch (148 CTAs x NR x RP doubles)
+  // beyond what stays L2-resident and leave fewer row splits for the reductions
+  const int Wg = std::min(Wmax, h->vglob_wmax > 0 ? h->vglob_wmax : 5);
   for (int W = Wg; W >= 1; --W)
     for (int rs = std::min(4, std::max(2, RBO_NWARPS / W)); rs >= 1; --rs)
       if (try_plan(W, rs, 0, 1)) return true;

@@ -10,7 +10,16 @@
 #        simulate_trajectory_mc(T, tp; ...)            rollout.jl:279-340
 #        simulate_trajectory_mc(T, tp, observable; ...) rollout.jl:342-404 (same body at HEAD, Q17)
 #        multistart_base_solve!(::Surrogate, xfinal; ...) rbf_optim.jl:103-134 (what both live drivers time)
-#      Julia's last-definition-wins makes this a drop-in: the drivers run unchanged.
+#      Julia's last-definition-wins makes this a drop-in: the drivers run unchanged;
+#   4. defines what utils.jl:235-265 calls but HEAD never defines -- simulate_adjoint_trajectory(surrogate, tp; ...) -- and re-defines
+#      stochastic_solve so that the surrogate, normals and starts stay RESIDENT on the device across the ascent iterations.
+#
+# Resident inputs: the handle remembers a fingerprint of the surrogate / normals / starts it holds and re-uploads only what changed
+# (a BO iteration changes the surrogate; an ascent iteration changes only x0). rbo_condition! appends an observation on the device.
+#
+# rand(dim) of solve_dual_y (rollout.jl:133, SURVEY.md hard part 2): reproduced EXACTLY by a two-phase call -- values and best
+# indices first, then rand(d) is drawn on the host only for the case-3 samples, j = t, t-1, .., 1, in sample order (the reference's
+# own consumption of the global RNG), then the device-resident x-path is replayed bitwise with the gradient (RBO_FLAG_REPLAY_TAPE).
 #
 # NOT RUN in the build environment (Julia is not installed there); the Python mirror
 # (rollout-bayesian-optimization_b200/api.py) drives the same C entry points in the tests.
@@ -43,7 +52,7 @@ end
 # ---- C ABI (include/rbo.h) ----------------------------------------------------------------------------------------
 struct RboSolverOpts
     maxit::Int32; maxtry::Int32
-    gtol::Float64; xtol::Float64; pred_tol::Float64; eta::Float64; lam_min::Float64; lam_up::Float64; lam_down::Float64
+    gtol::Float64; xtol::Float64; pred_tol::Float64; eta::Float64; delta0_box::Float64; delta0_ell::Float64; stol::Float64
 end
 mutable struct RboSummary
     mean::Float64; std::Float64; n_traj::Int32; n_failed::Int32
@@ -88,34 +97,94 @@ function _rbo_set_surrogate!(h::RboHandle, X::Matrix{Float64}, Ldata::Matrix{Flo
         _RBO_RULE_ID[g.name], _rbo_sigma_tol(g)))
 end
 
+# ---- resident inputs ----------------------------------------------------------------------------------------------------
+const _RBO_RESIDENT = Dict{Symbol, UInt}()   # fingerprints of what the handle currently holds
+_rbo_fp(xs...) = hash(xs)
+
+"""Uploads the base part of the fantasy surrogate unless the handle already holds it (same data, kernel, rule)."""
+function _rbo_sync_surrogate!(h::RboHandle, fs)
+    N = get_known_observations(fs)
+    fp = _rbo_fp(N, size(fs.X, 1), view(fs.X, :, 1:N), view(fs.y, 1:N), Vector{Float64}(fs.ψ.θ), fs.ψ.constructor, fs.g.name, fs.σn2)
+    get(_RBO_RESIDENT, :surrogate, UInt(0)) == fp && return
+    _rbo_set_surrogate!(h, fs.X, fs.L.data, fs.y, fs.cs[1], N, fs.ψ, fs.g, fs.σn2)
+    _RBO_RESIDENT[:surrogate] = fp
+    delete!(_RBO_RESIDENT, :normals); delete!(_RBO_RESIDENT, :starts)     # conservative: a new input dimension invalidates them
+end
+function _rbo_sync_normals!(h::RboHandle, rn::Array{Float64, 3})
+    fp = _rbo_fp(size(rn), rn[1], rn[end], sum(rn))   # content-based: a deepcopy of the TrajectoryParameters keeps the normals resident
+    get(_RBO_RESIDENT, :normals, UInt(0)) == fp && return
+    M = size(rn, 1)
+    _rbo_check(h, ccall((:rbo_set_normals, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cint, Cint), h.ptr, rn, M, size(rn, 3), 0, M))
+    _RBO_RESIDENT[:normals] = fp
+end
+function _rbo_sync_starts!(h::RboHandle, starts::Matrix{Float64})
+    fp = _rbo_fp(size(starts), sum(starts), starts[1], starts[end])
+    get(_RBO_RESIDENT, :starts, UInt(0)) == fp && return
+    _rbo_check(h, ccall((:rbo_set_starts, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), h.ptr, starts, size(starts, 2)))
+    _RBO_RESIDENT[:starts] = fp
+end
+
+"""condition!(s::Surrogate, x, y) (rbs.jl:214-222) mirrored on the device-resident surrogate: call it right after the host-side
+`condition!` of a BO iteration and the next simulate call uploads nothing (the fingerprint is refreshed by the caller's next sync)."""
+function rbo_condition!(x::Vector{Float64}, y::Float64)
+    h = _rbo_handle()
+    _rbo_check(h, ccall((:rbo_condition, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64), h.ptr, x, y))
+    delete!(_RBO_RESIDENT, :surrogate)   # the next sync compares against the host copy again (cheap: a hash of X, y)
+    return nothing
+end
+
+function _rbo_rollout!(h, tp, θ, fmini, mode::Int, flags::Int, dual, resolutions, gx, gθ, best_index, status, summary)
+    _rbo_check(h, ccall((:rbo_rollout, librbo), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint, Cint, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{RboSummary}),
+        h.ptr, tp.x0, θ, length(θ), tp.spatial_lbs, tp.spatial_ubs, tp.horizon, fmini, mode, flags,
+        dual === nothing ? C_NULL : dual, C_NULL, resolutions, gx === nothing ? C_NULL : gx, gθ === nothing ? C_NULL : gθ,
+        best_index === nothing ? C_NULL : best_index, C_NULL, status, summary))
+end
+
+function _rbo_first_error(status)
+    bad = findfirst(!=(0), status)
+    isnothing(bad) || error("sample $bad: " * get(_RBO_STATUS, Int(status[bad]), "error"))   # serial semantics: first failing sample
+end
+
 function _rbo_simulate(T::Trajectory, tp::TrajectoryParameters, inner_solve_xstarts::Matrix{Float64}, resolutions::Vector{Float64},
-                       spatial_gradients_container, hyperparameter_gradients_container)
+                       spatial_gradients_container, hyperparameter_gradients_container; flags::Int = 0)
     h = _rbo_handle()
     fs = get_fantasy_surrogate(T)
     set_start!(T, get_starting_point(tp))                                   # rollout.jl:287
-    N = get_known_observations(fs)
-    _rbo_set_surrogate!(h, fs.X, fs.L.data, fs.y, fs.cs[1], N, fs.ψ, fs.g, fs.σn2)
-    rn = tp.rnstream_sequence                                               # M x (d+1) x (h+1), column-major (trajectory.jl:47)
+    _rbo_sync_surrogate!(h, fs)
+    _rbo_sync_normals!(h, tp.rnstream_sequence)                             # M x (d+1) x (h+1), column-major (trajectory.jl:47)
+    _rbo_sync_starts!(h, inner_solve_xstarts)
     M, d, hor = tp.mc_iters, length(tp.x0), tp.horizon
-    _rbo_check(h, ccall((:rbo_set_normals, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cint, Cint), h.ptr, rn, M, size(rn, 3), 0, M))
-    _rbo_check(h, ccall((:rbo_set_starts, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), h.ptr, inner_solve_xstarts, size(inner_solve_xstarts, 2)))
     want_grad = !isnothing(spatial_gradients_container) && !isnothing(hyperparameter_gradients_container)  # rollout.jl:319
-    # rollout.jl:133 draws rand(dim) once per solve_dual_y call; here all of them are drawn up front, indexed
-    # [k, solve_index, sample] (the reference consumes them in a data-dependent order, SURVEY.md hard part 2)
-    dual = want_grad ? rand(d, max(hor, 1), M) : zeros(0)
     fmini = minimum(get_observations(get_base_surrogate(T)))               # rollout.jl:109,234 (zero-padded vector, Q2)
     status = zeros(Int32, M)
     summary = RboSummary()
     θ = Vector{Float64}(tp.θ)
-    _rbo_check(h, ccall((:rbo_rollout, librbo), Cint,
-        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint, Cint, Ptr{Float64}, Ptr{Float64},
-         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{RboSummary}),
-        h.ptr, tp.x0, θ, length(θ), tp.spatial_lbs, tp.spatial_ubs, hor, fmini, want_grad ? 1 : 0, 0,
-        want_grad ? dual : C_NULL, C_NULL, resolutions,
-        want_grad ? spatial_gradients_container : C_NULL, want_grad ? hyperparameter_gradients_container : C_NULL,
-        C_NULL, C_NULL, status, summary))
-    bad = findfirst(!=(0), status)
-    isnothing(bad) || error("sample $bad: " * get(_RBO_STATUS, Int(status[bad]), "error"))   # serial semantics: first failing sample
+    if want_grad && hor > 0
+        # phase 1: values and best indices (no gradient work)
+        best_index = zeros(Int32, M)
+        _rbo_rollout!(h, tp, θ, fmini, 0, flags, nothing, resolutions, nothing, nothing, best_index, status, summary)
+        _rbo_first_error(status)
+        # the reference's consumption of the global RNG (rollout.jl:259-262 -> :133): case-3 samples only, j = t:-1:1, sample order
+        dual = zeros(d, hor, M)
+        for m in 1:M
+            t = Int(best_index[m])
+            if resolutions[m] > 0.0 && t >= 1
+                for j in t:-1:1
+                    dual[:, j, m] = rand(d)
+                end
+            end
+        end
+        # phase 2: bitwise replay of the device-resident x-path with the adjoint (RBO_FLAG_REPLAY_TAPE = 8)
+        _rbo_rollout!(h, tp, θ, fmini, 1, flags | 8, dual, resolutions, spatial_gradients_container, hyperparameter_gradients_container,
+                      nothing, status, summary)
+    else
+        _rbo_rollout!(h, tp, θ, fmini, want_grad ? 1 : 0, flags, nothing, resolutions,
+                      want_grad ? spatial_gradients_container : nothing, want_grad ? hyperparameter_gradients_container : nothing,
+                      nothing, status, summary)
+    end
+    _rbo_first_error(status)
     μxθ = Distributions.mean(resolutions)                                  # rollout.jl:328-337
     σ_μxθ = Distributions.std(resolutions, mean = μxθ)
     if !want_grad
@@ -150,6 +219,7 @@ function simulate_trajectory_ghq(T::Trajectory, tp::TrajectoryParameters;
         spatial_gradients_container::Union{Nothing, Matrix{T1}} = nothing,
         hyperparameter_gradients_container::Union{Nothing, Matrix{T1}} = nothing) where T1 <: Real
     h = _rbo_handle()
+    empty!(_RBO_RESIDENT)                                                   # this call replaces the resident inputs directly
     fs = get_fantasy_surrogate(T)
     set_start!(T, get_starting_point(tp))                                   # rollout.jl:422
     N = get_known_observations(fs)
@@ -192,6 +262,7 @@ end
 # ExpectedTrajectoryOutput. Used by drivers that restart the stochastic ascent from a batch of x0 (utils.jl:235-265).
 function simulate_trajectory_mc_batch(T::Trajectory, tp::TrajectoryParameters, x0s::Matrix{Float64}; inner_solve_xstarts::Matrix{Float64})
     h = _rbo_handle()
+    empty!(_RBO_RESIDENT)
     fs = get_fantasy_surrogate(T)
     N = get_known_observations(fs)
     _rbo_set_surrogate!(h, fs.X, fs.L.data, fs.y, fs.cs[1], N, fs.ψ, fs.g, fs.σn2)
@@ -225,6 +296,7 @@ function multistart_base_solve!(surrogate::Surrogate, xfinal::Vector{T};
         return nothing
     end
     h = _rbo_handle()
+    empty!(_RBO_RESIDENT)
     N = get_observed(surrogate)
     _rbo_set_surrogate!(h, surrogate.X, surrogate.L.data, surrogate.y, surrogate.c[1:N], N, surrogate.ψ, surrogate.g, surrogate.σn2)
     _rbo_check(h, ccall((:rbo_set_starts, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), h.ptr, guesses, size(guesses, 2)))
@@ -238,3 +310,48 @@ end
 # gen_low_discrepancy_sequence (utils.jl:65-74) and generate_initial_guesses (utils.jl:145-153) keep their host
 # definitions from the reference checkout; librbo's device generators (rbo_generate_normals,
 # rbo_generate_initial_guesses) are used when the normals never have to visit the host (bench.py).
+
+
+# ---- the stochastic-gradient-ascent loop (utils.jl:235-265) ---------------------------------------------------------------
+# HEAD calls simulate_adjoint_trajectory(surrogate, tpc; ...), which is defined nowhere (SURVEY.md 0.3): it is the Monte-Carlo
+# estimator with its adjoint gradient on a trajectory built from the surrogate. The Trajectory / FantasySurrogate are cached per
+# surrogate so that the loop allocates them once; with the resident inputs above an ascent iteration uploads only x0.
+const _RBO_TRAJ = Ref{Any}(nothing)
+function _rbo_trajectory(surrogate::Surrogate, tp::TrajectoryParameters)
+    key = (objectid(surrogate), get_observed(surrogate), tp.horizon)
+    c = _RBO_TRAJ[]
+    if c === nothing || c[1] != key
+        fs = FantasySurrogate(surrogate, tp.horizon)
+        T = Trajectory(surrogate, fs; start = get_starting_point(tp), hypers = get_hyperparameters(tp), horizon = tp.horizon)
+        _RBO_TRAJ[] = (key, T)
+        return T
+    end
+    return c[2]
+end
+
+function simulate_adjoint_trajectory(surrogate::Surrogate, tp::TrajectoryParameters;
+        inner_solve_xstarts::Matrix{Float64}, resolutions::Vector{Float64},
+        spatial_gradients_container::Union{Nothing, Matrix{Float64}} = nothing,
+        hyperparameter_gradients_container::Union{Nothing, Matrix{Float64}} = nothing)
+    T = _rbo_trajectory(surrogate, tp)
+    return _rbo_simulate(T, tp, inner_solve_xstarts, resolutions, spatial_gradients_container, hyperparameter_gradients_container)
+end
+
+# stochastic_solve (utils.jl:235-265), same signature and iteration cap (50); only the undefined callee is resolved. Every iteration
+# is one simulate_adjoint_trajectory with the same normals (common random numbers) and a new x0.
+function stochastic_solve(; optimizer::StochasticGradientAscent, surrogate::Surrogate, tp::TrajectoryParameters, es::ExperimentSetup,
+                          start::AbstractVector)
+    tpc = deepcopy(tp)
+    set_starting_point!(tpc, deepcopy(start))
+    for iter in 1:50
+        eto = simulate_adjoint_trajectory(surrogate, tpc,
+            inner_solve_xstarts = get_starts(es), resolutions = get_container(es, symbol = :f),
+            spatial_gradients_container = get_container(es, symbol = :grad_f),
+            hyperparameter_gradients_container = get_container(es, symbol = :grad_hypers))
+        if eswavs(∇f = gradient(eto), var_∇f = std_gradient(eto) .^ 2, sample_size = tp.mc_iters)   # utils.jl:114-123
+            break
+        end
+        update!(optimizer, x = get_starting_point(tpc), ∇f = gradient(eto))                            # optimizers.jl:16-22, 48-75
+    end
+    return get_starting_point(tpc)
+end

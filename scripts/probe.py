@@ -12,7 +12,7 @@ def main():
     ap.add_argument("name"); ap.add_argument("M", type=int)
     ap.add_argument("--oracle", type=int, default=0); ap.add_argument("--large-n", action="store_true")
     ap.add_argument("--slots", type=int, default=None); ap.add_argument("--value-only", action="store_true")
-    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--reps", type=int, default=2); ap.add_argument("--rs-cap", type=int, default=0)
     a = ap.parse_args()
     pkg = g.load_package()
     wl = pkg.problems.make_workload(a.name, M=a.M)
@@ -20,6 +20,8 @@ def main():
     eng = pkg.RolloutEngine(0)
     if a.large_n or a.slots is not None:
         eng.set_tuning(large_n=a.large_n or None, large_n_slots=a.slots)
+    if a.rs_cap:
+        eng.handle.check(eng.lib.rbo_set_tuning(eng.handle.h, 4, a.rs_cap))
     t0 = time.time(); eng.set_surrogate(pkg.FantasySurrogate(sur, wl.h)); t_set = time.time() - t0
     eng.generate_normals(a.M, wl.h + 1)
     starts = pkg.generate_initial_guesses(wl.S, wl.lbs, wl.ubs)
