@@ -310,7 +310,7 @@ def main():
     mean_v, std_v, gm, gs = finalize(sums.cpu().numpy())
     summ = eng.rollout_device(wl.x0, wl.theta, wl.lbs, wl.ubs, h, fmini, mode, dual_dirs_ptr=dd_dev.data_ptr() if want_grad else None, want_summary=True)
     acct = torch.tensor([summ.flops, summ.flops_executed, float(summ.n_evals), float(summ.n_failed), summ.kernel_ms], dtype=torch.float64, device=dev)
-    kmax = torch.tensor([summ.kernel_ms], dtype=torch.float64, device=dev)
+    kmax = torch.tensor([summ.kernel_ms, summ.tail_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(acct)
         dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
@@ -363,7 +363,7 @@ def main():
     if rank != 0:
         return
 
-    kernel_ms = float(kmax.item())
+    kernel_ms, tail_ms = float(kmax[0].item()), float(kmax[1].item())
     achieved_tf = acct[0] / (kernel_ms * 1e-3) / 1e12  # whole-job flops / slowest rank's kernel time
     achieved_per_gpu = achieved_tf / world
     cpu, parity = None, None
@@ -404,7 +404,9 @@ def main():
                      "flops_per_launch": acct[0] / world, "flops_executed_per_launch": acct[1] / world,
                      "frac_executed": acct[1] / world / (kernel_ms * 1e-3) / 1e12 / peak_tf,
                      "peak_source": "rbo_fp64_peak: dense FP64 FMA micro-benchmark in this process (MEASURED_PEAKS.json has no FP64 figure)",
-                     "kernel_share_of_step": kernel_ms / ms_per_step},
+                     "kernel_share_of_step": kernel_ms / ms_per_step,
+                     # tail of the persistent grid on the slowest rank: last CTA to finish minus the median CTA (device globaltimer)
+                     "tail_ms": tail_ms, "tail_share_of_kernel": tail_ms / kernel_ms},
         "cpu_baseline": cpu,
         "parity_in_bench": parity,
         "estimate": {"mean": mean_v, "std": std_v, "grad_x_mean": gm.tolist(), "n_failed": int(acct[3]),

@@ -90,6 +90,7 @@ typedef struct {
   double flops_executed;        /* FP64 flops this implementation executes for the same work (fewer: forward-only solves) */
   int64_t n_evals;              /* acquisition evaluations performed by the inner solves */
   int32_t gpu_launches;         /* kernels launched by this call */
+  double tail_ms;               /* tail of the persistent grid: last CTA to finish minus the median CTA (device %globaltimer) */
 } rbo_summary;
 
 /* ---- life cycle ------------------------------------------------------------------------------ */
@@ -110,7 +111,10 @@ int rbo_set_htol(rbo_handle* h, double htol);
 /* Execution knobs (results do not depend on them beyond rounding): RBO_TUNE_LARGE_N != 0 forces the large-n variant of the
  * kernel -- work matrix in an L2-resident global scratch instead of shared memory; chosen automatically when a problem does
  * not fit 227 KB (e.g. n = 1000, d = 20) -- and RBO_TUNE_LARGE_N_SLOTS caps its start slots per round (0 = default). */
-enum { RBO_TUNE_LARGE_N = 1, RBO_TUNE_LARGE_N_SLOTS = 2 };
+enum { RBO_TUNE_LARGE_N = 1, RBO_TUNE_LARGE_N_SLOTS = 2,
+       RBO_TUNE_LPT = 3 /* default 1: hand the trajectories out longest-first, using the evaluation counts of the previous launch on the
+                           same samples as the cost estimate (scheduling only: per-trajectory results do not depend on it) */,
+       RBO_TUNE_ROW_SPLITS = 4 /* cap (1..4, 0 = default) on the row splits of the Gram reductions: plan experiments */ };
 int rbo_set_tuning(rbo_handle* h, int key, int value);
 
 /* ---- inputs (resident on the device until replaced) ------------------------------------------ */

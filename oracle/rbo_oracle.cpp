@@ -987,7 +987,7 @@ void orc_default_solver_opts(orc_solver_opts* o) {
   o->eta = 0.1;
   o->delta0_box = 0.5;
   o->delta0_ell = 1.0;
-  o->stol = 1e-6;
+  o->stol = 1e-5;
 }
 
 int orc_rollout(const orc_problem* p, orc_outputs* out) {

@@ -21,7 +21,7 @@ class SolverOpts(C.Structure):
 class Summary(C.Structure):
     _fields_ = [("mean", C.c_double), ("std", C.c_double), ("n_traj", C.c_int32), ("n_failed", C.c_int32),
                 ("kernel_ms", C.c_double), ("flops", C.c_double), ("flops_executed", C.c_double),
-                ("n_evals", C.c_int64), ("gpu_launches", C.c_int32)]
+                ("n_evals", C.c_int64), ("gpu_launches", C.c_int32), ("tail_ms", C.c_double)]
 
 
 # every symbol include/rbo.h declares: name -> (restype, argtypes)

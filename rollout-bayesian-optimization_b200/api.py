@@ -410,12 +410,14 @@ class RolloutEngine:
             setattr(o, k, v)
         self.handle.check(self.lib.rbo_set_solver_opts(self.handle.h, C.byref(o)))
 
-    def set_tuning(self, large_n=None, large_n_slots=None):
+    def set_tuning(self, large_n=None, large_n_slots=None, lpt=None):
         """Execution knobs of rbo_set_tuning: force the large-n kernel variant / cap its start slots."""
         if large_n is not None:
             self.handle.check(self.lib.rbo_set_tuning(self.handle.h, 1, int(bool(large_n))))
         if large_n_slots is not None:
             self.handle.check(self.lib.rbo_set_tuning(self.handle.h, 2, int(large_n_slots)))
+        if lpt is not None:
+            self.handle.check(self.lib.rbo_set_tuning(self.handle.h, 3, int(bool(lpt))))
 
     def set_htol(self, htol):
         self.handle.check(self.lib.rbo_set_htol(self.handle.h, float(htol)))

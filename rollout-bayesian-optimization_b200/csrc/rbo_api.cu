@@ -23,6 +23,7 @@ __global__ void rbo_stats_kernel(const double* values, const double* gx, const d
                                  const int* status, int M, int d, int nth, int h, double* sums);
 __global__ void rbo_fp64_peak_kernel(double* out, int iters);
 __global__ void rbo_gather_sums_kernel(const double* sums, int need, int idx_failed, const int* work_counter, double* out);
+__global__ void rbo_lpt_order_kernel(const int* n_evals, const int* grad_case, const int* best_index, int M, int hh, int* order);
 // surrogate_kernels.cu
 __global__ void rbo_trinv_kernel(const double* L, int N, int N32, double* Linv, int ldi);
 __global__ void rbo_pack_fwd_kernel(const double* Linv, int ldi, int nb32, double* Lf);
@@ -82,7 +83,12 @@ struct rbo_handle {
   double *t_mu = nullptr, *t_sigma = nullptr, *t_dmu = nullptr, *t_dsigma = nullptr, *t_Halpha = nullptr;
   size_t cap_tex = 0;  // trajectories x steps the extended tape holds
   bool tex_valid = false;
-  bool xs_valid = false;  // the x-path of the last rollout is on the device (RBO_FLAG_REPLAY_TAPE)
+  bool xs_valid = false;
+  int* order = nullptr;     // longest-first order of the trajectories of the last launch (scheduling hint for the next one)
+  size_t cap_order = 0;
+  int order_M = 0;          // 0: no valid order
+  int lpt = 1;              // RBO_TUNE_LPT
+  unsigned long long* cta_done = nullptr;  // the x-path of the last rollout is on the device (RBO_FLAG_REPLAY_TAPE)
   // resident surrogate in its canonical device form (rbo_set_surrogate / rbo_condition): L0^-1 row-major with pitch ldi,
   // the observation sites point-major, work vectors
   double *Ld = nullptr, *Linv = nullptr, *Xpts = nullptr, *wk = nullptr;
@@ -136,7 +142,7 @@ void rbo_default_solver_opts(rbo_solver_opts* o) {
   o->eta = 0.1;
   o->delta0_box = 0.5;
   o->delta0_ell = 1.0;
-  o->stol = 1e-6;
+  o->stol = 1e-5;
 }
 
 const char* rbo_last_error(const rbo_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -169,6 +175,7 @@ int rbo_create(rbo_handle** out, int device_id) {
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
   CKC(cudaMalloc((void**)&h->work_counter, 16 * sizeof(int)));  // [0] trajectory scheduler, [1..2] kernel watchdog flags
+  CKC(cudaMalloc((void**)&h->cta_done, 1024 * sizeof(unsigned long long)));
   CKC(cudaMalloc((void**)&h->sobol_dirs, sizeof(rbo_sobol_dirs_host)));
   CKC(cudaMemcpy(h->sobol_dirs, rbo_sobol_dirs_host, sizeof(rbo_sobol_dirs_host), cudaMemcpyHostToDevice));
   CKC(cudaFuncSetAttribute(rbo_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
@@ -184,7 +191,7 @@ int rbo_destroy(rbo_handle* h) {
   cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->Xb, h->yb, h->c0, h->u0, h->Lf, h->Lb, h->Lbf, h->x0_batch, h->rn, h->starts, h->sobol_dirs, h->values, h->grad_x, h->grad_theta, h->xs, h->ys,
                   h->gys, h->alphas, h->best_index, h->grad_case, h->status, h->n_evals, h->start_status, h->start_iters, h->work_counter, h->sums,
-                  h->dual_dirs, h->x_forced, h->cs_tape, h->gh_nodes, h->gh_weights, h->Vscratch, h->Bscratch, h->Ld, h->Linv, h->Xpts, h->wk, h->dstat, h->t_mu, h->t_sigma, h->t_dmu, h->t_dsigma, h->t_Halpha};
+                  h->dual_dirs, h->x_forced, h->cs_tape, h->gh_nodes, h->gh_weights, h->Vscratch, h->Bscratch, h->Ld, h->Linv, h->Xpts, h->wk, h->dstat, h->t_mu, h->t_sigma, h->t_dmu, h->t_dsigma, h->t_Halpha, h->order, h->cta_done};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -212,7 +219,8 @@ int rbo_set_tuning(rbo_handle* h, int key, int value) {
   switch (key) {
     case RBO_TUNE_LARGE_N: h->force_vglob = value != 0; return RBO_SUCCESS;
     case RBO_TUNE_LARGE_N_SLOTS: if (value < 0 || value > RBO_NCONS) break; h->vglob_wmax = value; return RBO_SUCCESS;
-    case 4: if (value < 0 || value > 4) break; h->rs_cap = value; return RBO_SUCCESS;  // undocumented: row-split cap (plan experiments)
+    case RBO_TUNE_LPT: h->lpt = value != 0; h->order_M = 0; return RBO_SUCCESS;
+    case RBO_TUNE_ROW_SPLITS: if (value < 0 || value > 4) break; h->rs_cap = value; return RBO_SUCCESS;
     default: break;
   }
   return fail(h, RBO_ERR_ARG, "rbo_set_tuning: unknown key %d or value %d out of range", key, value);
@@ -406,7 +414,7 @@ int rbo_set_normals(rbo_handle* h, const double* rn, int M_total, int hp1, int m
   // strided slice [m_begin, m_begin+m_count) of the sample-fastest tensor
   CK(h, cudaMemcpy2DAsync(h->rn, (size_t)m_count * 8, rn + m_begin, (size_t)M_total * 8, (size_t)m_count * 8, (size_t)q1 * hp1, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
-  h->M = m_count; h->hp1 = hp1;
+  h->M = m_count; h->hp1 = hp1; h->order_M = 0;
   return RBO_SUCCESS;
 }
 
@@ -423,7 +431,7 @@ int rbo_generate_normals(rbo_handle* h, int M_total, int hp1, int m_begin, int m
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 8);
   rbo_normals_kernel<<<blocks, 256, 0, h->stream>>>(h->sobol_dirs, h->rn, M_total, h->d, hp1, m_begin, m_count);
   CK(h, cudaGetLastError());
-  h->M = m_count; h->hp1 = hp1;
+  h->M = m_count; h->hp1 = hp1; h->order_M = 0;
   return RBO_SUCCESS;
 }
 
@@ -599,6 +607,9 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
     h->tex_valid = true;
   }
   const int grid = std::min(M, h->num_sms);
+  // longest-first hand-out when the previous launch ran the same trajectories (same normals, nearby x0): only worth it beyond two waves
+  P.order = (h->lpt && !myopic && h->order_M == M && M > 2 * grid && !(flags & RBO_FLAG_TEACHER_FORCED)) ? h->order : nullptr;
+  P.cta_done = grid <= 1024 ? h->cta_done : nullptr;
   {
     size_t need = (size_t)grid * (horizon + 2) * pc.NR;
     if (h->tape_cap < need) { CK(h, dev_realloc(&h->cs_tape, need)); h->tape_cap = need; }
@@ -620,6 +631,12 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
                                               h->n_evals, h->best_index, h->grad_case, h->status, M, h->d, ntheta, horizon, h->sums);
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(h->ev1, h->stream));
+  if (h->lpt && !myopic && horizon > 0 && M > 2 * grid && !(flags & RBO_FLAG_TEACHER_FORCED)) {
+    CK(h, dev_reserve(&h->order, &h->cap_order, (size_t)M));
+    rbo_lpt_order_kernel<<<1, 1024, 0, h->stream>>>(h->n_evals, h->grad_case, h->best_index, M, std::max(horizon, 1), h->order);
+    CK(h, cudaGetLastError());
+    h->order_M = M;
+  } else if (!(flags & RBO_FLAG_TEACHER_FORCED)) h->order_M = 0;
   h->last_h = horizon; h->last_mode = mode; h->last_nth = ntheta;
   h->xs_valid = !myopic;
   if (want_summary && summary) {
@@ -639,7 +656,14 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
     summary->mean = n > 0 ? sums[1] / n : NAN;
     summary->std = n > 1 ? std::sqrt(sums[2] / (n - 1)) : NAN;
     summary->kernel_ms = ms;
-    summary->gpu_launches = 2;
+    summary->gpu_launches = 2 + (h->order_M == M ? 1 : 0);
+    summary->tail_ms = 0.0;
+    if (P.cta_done) {
+      std::vector<unsigned long long> td(grid);
+      CK(h, cudaMemcpy(td.data(), h->cta_done, (size_t)grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      std::sort(td.begin(), td.end());
+      summary->tail_ms = (double)(td.back() - td[grid / 2]) * 1e-6;  // last CTA to finish minus the median CTA
+    }
     const double* ev = sums.data() + 1 + 3 * nrows;
     const double* hist = ev + hh;
     summary->n_failed = (int)hist[horizon + 2];

@@ -1337,7 +1337,12 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) RBO_KERNEL_NAME(const __grid_c
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) si[I_M] = atomicAdd(P.work_counter, 1);
+    if (tid == 0) {
+      // dynamic scheduler; with an order from the previous launch the trajectories are handed out longest-first (LPT), which
+      // shortens the tail of the persistent grid -- the per-trajectory results do not depend on the order
+      const int i = atomicAdd(P.work_counter, 1);
+      si[I_M] = (i < P.M) ? (P.order ? P.order[i] : i) : P.M;
+    }
     __syncthreads();
     const int m = si[I_M];
     if (m >= P.M) break;
@@ -1745,6 +1750,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) RBO_KERNEL_NAME(const __grid_c
     if (tid == 0 && P.status) P.status[m] = si[I_TSTATUS];
   }
   k.pipe_fini();
+  if (tid == 0 && P.cta_done) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); P.cta_done[blockIdx.x] = t; }
 }
 
 #if !RBO_VGLOB
@@ -1863,6 +1869,38 @@ __global__ void rbo_stats_kernel(const double* __restrict__ values, const double
     double tot = block_sum(acc);
     if (threadIdx.x == 0) hist[t + (t > h ? 1 : 0)] = tot;
   }
+}
+
+// Longest-processing-time order for the NEXT launch on the same samples (common random numbers: the outer ascent loop and the
+// bench re-evaluate the same trajectories at a nearby x0, so the evaluation counts of this launch predict the next one's costs):
+// counting sort of the trajectories by descending cost. One CTA; ties in arbitrary order (scheduling only).
+__global__ void rbo_lpt_order_kernel(const int* __restrict__ n_evals, const int* __restrict__ grad_case, const int* __restrict__ best_index, int M, int hh,
+                                     int* __restrict__ order) {
+  constexpr int NB = 2048;
+  __shared__ int hist[NB];
+  __shared__ int smax;
+  auto cost = [&](int m) {
+    int c = 1;
+    for (int j = 0; j < hh; ++j) c += n_evals[(size_t)m * hh + j];
+    if (grad_case[m] == 3) { const int t = best_index[m]; c += 2 * t * (t + 1); }  // the adjoint re-evaluates t policy solves with i perturbation solves each
+    return c;
+  };
+  if (threadIdx.x == 0) smax = 1;
+  for (int i = threadIdx.x; i < NB; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  int mx = 1;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) mx = max(mx, cost(m));
+  atomicMax(&smax, mx);
+  __syncthreads();
+  const double scale = (double)(NB - 1) / (double)smax;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) atomicAdd(&hist[(int)(cost(m) * scale)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {  // exclusive offsets in DESCENDING bucket order
+    int run = 0;
+    for (int b = NB - 1; b >= 0; --b) { const int c = hist[b]; hist[b] = run; run += c; }
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < M; m += blockDim.x) order[atomicAdd(&hist[(int)(cost(m) * scale)], 1)] = m;
 }
 
 // out = [sums[0 .. need), number of failed trajectories, kernel watchdog flag]: the vector the multi-GPU all-reduce sums

@@ -56,8 +56,8 @@ struct RboSolverOpts
 end
 mutable struct RboSummary
     mean::Float64; std::Float64; n_traj::Int32; n_failed::Int32
-    kernel_ms::Float64; flops::Float64; flops_executed::Float64; n_evals::Int64; gpu_launches::Int32
-    RboSummary() = new(0, 0, 0, 0, 0, 0, 0, 0, 0)
+    kernel_ms::Float64; flops::Float64; flops_executed::Float64; n_evals::Int64; gpu_launches::Int32; tail_ms::Float64
+    RboSummary() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
 end
 
 const _RBO_KERNEL_ID = IdDict{Any, Cint}(Matern12 => 0, Matern32 => 1, Matern52 => 2, SquaredExponential => 3, Periodic => 4)

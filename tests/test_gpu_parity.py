@@ -791,3 +791,23 @@ def test_two_phase_call_reproduces_the_reference_rng_consumption(pkg, orc):
     err = np.max(np.abs(gx - ref["grad_x"]) / gscale, axis=0)
     assert np.mean(err[c3] < 1e-6) >= 0.97 and np.all(err[~c3] < 1e-6), np.sort(err)[-4:]
     assert np.isclose(pkg.mean(eto), res.mean())
+
+
+def test_longest_first_schedule_does_not_change_results(pkg, orc):
+    """RBO_TUNE_LPT: the second launch on the same samples hands the trajectories out longest-first (evaluation counts of the previous
+    launch). Scheduling only: per-trajectory results are bitwise those of the natural order; the tail metric is reported."""
+    wl, sur, rn, starts, dd = setup(pkg, orc, "C2", M=600, S=6)
+    outs = []
+    for lpt in (False, True):
+        eng = pkg.RolloutEngine(0)
+        try:
+            eng.set_tuning(lpt=lpt)
+            eng.set_surrogate(pkg.FantasySurrogate(sur, wl.h)); eng.set_normals(rn); eng.set_starts(starts)
+            for rep in range(2):  # the second launch uses the order computed by the first
+                v, gx, gt = np.zeros(wl.M), np.zeros((wl.d, wl.M), order="F"), np.zeros((1, wl.M), order="F")
+                s = eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), v, gx, gt, dual_dirs=dd)
+            outs.append((v, gx, s.tail_ms, s.kernel_ms))
+        finally:
+            eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] >= 0.0 and outs[1][2] >= 0.0 and outs[1][2] < outs[1][3]
