@@ -39,7 +39,7 @@ namespace rbo {
 __device__ unsigned long long g_phase_cycles[16];
 __device__ unsigned long long g_aux_cycles[16];  // tri_solve sub-phases seen by warp 0: [8*bwd + {setup, fan-pre, chunks, mma, diag, fan-post, calls}]
 #define AUX_T(v) long long v = clock64()
-#define AUX_ADD(i, t0) do { if (threadIdx.x == 0) atomicAdd(&g_aux_cycles[(FWD ? 0 : 8) + (i)], (unsigned long long)(clock64() - (t0))); } while (0)
+#define AUX_ADD(i, t0) do { } while (0)
 #define PT_DECL long long pt_t0 = clock64()
 #define PT_MARK(i) do { if (threadIdx.x == 0) { long long t1_ = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(t1_ - pt_t0)); pt_t0 = t1_; } } while (0)
 #else
@@ -673,7 +673,6 @@ struct K {
     AUX_T(ts0_);
     AUX_ADD(0, ts0_);
 #ifdef RBO_PHASE_TIMERS
-    if (tid == 0) atomicAdd(&g_aux_cycles[(FWD ? 0 : 8) + 6], 1ull);
 #endif
     if (warp == RBO_NCONS) {
       // ---------------- producer warp ----------------
@@ -1279,6 +1278,7 @@ struct K {
         slot_logic_warp(sl, single);
 #ifdef RBO_PHASE_TIMERS
         if (tid == 0) atomicAdd(&g_phase_cycles[14], (unsigned long long)(clock64() - ta_));
+        if (lane == 0) { long long dt_ = clock64() - ta_; int b_ = (int)(dt_ / 4000); atomicAdd(&g_aux_cycles[b_ > 15 ? 15 : b_], 1ull); }  // duration histogram of the solver step
 #endif
       }
       __syncthreads();

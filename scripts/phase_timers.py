@@ -6,8 +6,8 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import __graft_entry__ as g
 
-NAMES = ["fill_columns", "reduce_pre", "fwd_solve", "reduce_post", "bwd_solve", "reduce_hess", "logic team: solver steps (shared-memory build: overlapped)", "compute team waits for logic",
-         "logic team: assemble", "logic team waits for compute", "draw+condition", "adjoint", "wait_full(fwd,w0)", "wait_full(bwd,w0)", "  logic:solver(w0) [large-n build]", "rounds"]
+NAMES = ["fill_columns", "reduce_pre", "fwd_solve", "reduce_post", "bwd_solve", "reduce_hess", "per-start logic (all slots: assemble + solver step, slowest warp)", "bookkeeping",
+         "  logic: assemble (warp 0)", "round gap", "draw+condition", "adjoint", "wait_full(fwd,w0)", "wait_full(bwd,w0)", "  logic: solver step (warp 0)", "rounds"]
 
 def main(name="C3", M=296, large_n=False):
     pkg = g.load_package()
@@ -40,11 +40,9 @@ def main(name="C3", M=296, large_n=False):
         if NAMES[i] != "-":
             print(f"  {NAMES[i]:<60} {100 * out[i] / tot:5.1f}%   {out[i] / max(rounds, 1):9.0f} cycles/round")
     fa(eng.handle.h, aux, 0)
-    AN = ["setup", "fan-pre", "chunk loop", "  mma+store", "  diag sync+store", "-", "calls(x cycles~1)", "-"]
-    for half, nm in ((0, "fwd"), (8, "bwd")):
-        for i in range(7):
-            if AN[i] != "-":
-                print(f"  {nm} {AN[i]:<18} {aux[half + i] / max(rounds, 1):9.0f} cycles/round")
+    tot_calls = sum(aux[i] for i in range(16))
+    print("  per-start solver step (slot_logic_warp) duration histogram, bins of 4k cycles (last bin: >= 60k): " +
+          " ".join(f"{100 * aux[i] / max(tot_calls, 1):.1f}%" for i in range(16)))
     eng.close()
 
 if __name__ == "__main__":
