@@ -193,6 +193,11 @@ int rbo_rollout_device(rbo_handle* h, const double* x0, const double* theta, int
  * watchdog != 0 if the kernel reported a stuck pipeline or an inner solve beyond its evaluation bound.
  * M2 is the centred sum of squares around this handle's own mean (two-pass, as rollout.jl:328-337). */
 int rbo_partial_sums_device(rbo_handle* h, double* sums_device, int len);
+/* The same vector on the HOST, for a single-process multi-GPU host (e.g. Julia: one handle per device, rbo_rollout_device on each --
+ * the launches are asynchronous --, then this call per handle, an element-wise sum, rbo_finalize_sums): waits for this handle's launch. */
+int rbo_partial_sums_host(rbo_handle* h, double* sums, int len);
+/* Per-trajectory results of the last rollout of this handle (its shard of the containers): any pointer may be NULL. */
+int rbo_get_results(rbo_handle* h, double* values, double* grad_x, double* grad_theta, int32_t* best_index, int32_t* grad_case, int32_t* status);
 /* Host-side merge of all-reduced sums into means / corrected sample stds (Chan's pairwise update). Returns RBO_ERR_NUMERIC
  * when any rank reported a failed trajectory or a watchdog flag (the reference would have thrown): no silent estimates. */
 int rbo_finalize_sums(const double* sums, int d, int ntheta, double* mean, double* std, double* gx_mean,

@@ -51,6 +51,8 @@ SYMBOLS = {
     "rbo_rollout_batch": (C.c_int, [C.c_void_p, _dp, C.c_int, _dp, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_int, _dp, _dp, _dp, _dp, _ip,
                                     C.POINTER(Summary)]),
     "rbo_partial_sums_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "rbo_partial_sums_host": (C.c_int, [C.c_void_p, _dp, C.c_int]),
+    "rbo_get_results": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _ip, _ip, _ip]),
     "rbo_finalize_sums": (C.c_int, [_dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
     "rbo_get_tape": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _ip, _ip, _ip]),
     "rbo_get_tape_ex": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp]),

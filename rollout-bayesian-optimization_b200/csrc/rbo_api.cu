@@ -491,7 +491,7 @@ static int ensure_outputs(rbo_handle* h, int M, int hor, int S, int d, int nth) 
   CK(h, dev_realloc(&h->start_status, (size_t)M * hh * S));
   CK(h, dev_realloc(&h->start_iters, (size_t)M * hh * S));
   h->sums_len = 1 + 3 * (1 + d + nth) + hh + (hor + 2) + 2;
-  CK(h, dev_realloc(&h->sums, (size_t)h->sums_len));
+  CK(h, dev_realloc(&h->sums, (size_t)h->sums_len + 1 + 3 * (1 + d + nth) + 2));  // + the gathered partial-sums vector (rbo_partial_sums_host)
   h->outM = M; h->outh = hor; h->outS = S; h->outd = d; h->outnth = nth;
   return RBO_SUCCESS;
 }
@@ -777,6 +777,35 @@ int rbo_partial_sums_device(rbo_handle* h, double* sums_device, int len) {
   const int idx_failed = need + hh + (h->outh + 2);  // sums layout of rbo_stats_kernel: rows, evaluations per step, case-3 histogram, failures
   rbo_gather_sums_kernel<<<1, 64, 0, h->stream>>>(h->sums, need, idx_failed, h->work_counter, sums_device);
   CK(h, cudaGetLastError());
+  return RBO_SUCCESS;
+}
+
+int rbo_partial_sums_host(rbo_handle* h, double* sums, int len) {
+  if (!h || !sums) return RBO_ERR_ARG;
+  const int need = 1 + 3 * (1 + h->outd + h->outnth) + 2;
+  if (!h->sums || len < need) return fail(h, RBO_ERR_ARG, "rbo_partial_sums_host: need %d doubles (1 + 3 (1 + d + ntheta) + 2)", need);
+  CK(h, cudaSetDevice(h->device));
+  double* tmp = h->sums + h->sums_len;  // the sums buffer is allocated with room for the gathered vector
+  int rc = rbo_partial_sums_device(h, tmp, need);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(sums, tmp, (size_t)need * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));  // this is the call that waits for the (asynchronous) rbo_rollout_device of this handle
+  return RBO_SUCCESS;
+}
+
+int rbo_get_results(rbo_handle* h, double* values, double* grad_x, double* grad_theta, int32_t* best_index, int32_t* grad_case, int32_t* status) {
+  if (!h) return RBO_ERR_ARG;
+  if (h->outh < 0 || h->outM <= 0) return fail(h, RBO_ERR_STATE, "rbo_get_results: no rollout has run");
+  CK(h, cudaSetDevice(h->device));
+  const size_t M = h->outM;
+  if (values) CK(h, cudaMemcpyAsync(values, h->values, M * 8, cudaMemcpyDeviceToHost, h->stream));
+  if ((grad_x || grad_theta) && h->last_mode != RBO_MODE_VALUE_GRAD) return fail(h, RBO_ERR_STATE, "rbo_get_results: the last rollout computed no gradients");
+  if (grad_x) CK(h, cudaMemcpyAsync(grad_x, h->grad_x, M * h->outd * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (grad_theta) CK(h, cudaMemcpyAsync(grad_theta, h->grad_theta, M * h->outnth * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (best_index) CK(h, cudaMemcpyAsync(best_index, h->best_index, M * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (grad_case) CK(h, cudaMemcpyAsync(grad_case, h->grad_case, M * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (status) CK(h, cudaMemcpyAsync(status, h->status, M * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
   return RBO_SUCCESS;
 }
 

@@ -25,6 +25,13 @@
 #ifndef RBO_VGLOB
 #define RBO_VGLOB 0
 #endif
+// The large-n build walks the work matrix (and the base locations) in global memory: its row loops are unrolled deeper so that
+// more L2 loads are in flight per warp; the shared-memory build sits at the register cap and keeps the shallow unroll.
+#if RBO_VGLOB
+#define RBO_ROW_UNROLL _Pragma("unroll 4")
+#else
+#define RBO_ROW_UNROLL _Pragma("unroll 2")
+#endif
 #if RBO_VGLOB
 #define RBO_KERNEL_NAME rbo_rollout_kernel_largen
 #define g_phase_cycles g_phase_cycles_largen
@@ -335,6 +342,9 @@ struct K {
       const double* xc = base ? (P.xsm ? Xs + j : P.Xb + j) : Xf + (j - P.N8) * d;
       const int xst = base ? (P.xsm ? P.XP : P.N8) : 1;
       double rho2 = 0.0;
+#if RBO_VGLOB
+#pragma unroll 4
+#endif
       for (int p = 0; p < d; ++p) { double r = x[p] - xc[p * xst]; rho2 = fma(r, r, rho2); }
       double psi, a, b, gb;
       if (P.kern.id == RBO_KERNEL_MATERN52) {
@@ -348,6 +358,9 @@ struct K {
         kern_radial(P.kern, rho2, psi, a, b, gb);
       }
       row[0] = psi;
+#if RBO_VGLOB
+#pragma unroll 4
+#endif
       for (int p = 0; p < d; ++p) row[1 + p] = b * (x[p] - xc[p * xst]);
       row[d + 1] = a;
       row[d + 2] = b;
@@ -395,7 +408,7 @@ struct K {
       const int step = 4 * RS * RP, nfull = nrows & ~3;
       const double* row = V + (4 * rs + tg) * RP;
       int j0 = 4 * rs;
-#pragma unroll 2
+RBO_ROW_UNROLL
       for (; j0 < nfull; j0 += 4 * RS, row += step) {
         const double a0 = row[ca0], b0 = row[cb0];
         dmma(c00[0], c00[1], a0, b0);
@@ -484,7 +497,7 @@ struct K {
       const double* row = V + (j0 + tg) * RP;
       if (P.xsm) {
         const double* xs = Xs + j0 + tg;
-#pragma unroll 2
+RBO_ROW_UNROLL
         for (; j0 < nbase4; j0 += jstep, row += jstep * RP, xs += jstep) {
           const double rp0 = xp0 - xs[op0], rp1 = xp1 - xs[op1];
           const double rq0 = diag ? rp0 : xq0 - xs[oq0], rq1 = diag ? rp1 : xq1 - xs[oq1];
@@ -492,7 +505,7 @@ struct K {
         }
       } else {
         const double* xs = P.Xb + j0 + tg;
-#pragma unroll 2
+RBO_ROW_UNROLL
         for (; j0 < nbase4; j0 += jstep, row += jstep * RP, xs += jstep) {
           const double rp0 = xp0 - __ldg(xs + op0), rp1 = xp1 - __ldg(xs + op1);
           const double rq0 = diag ? rp0 : xq0 - __ldg(xs + oq0), rq1 = diag ? rp1 : xq1 - __ldg(xs + oq1);

@@ -355,3 +355,78 @@ function stochastic_solve(; optimizer::StochasticGradientAscent, surrogate::Surr
     end
     return get_starting_point(tpc)
 end
+
+
+# ---- single-process multi-GPU (SURVEY.md section 8e) -----------------------------------------------------------------------
+# One handle per device; contiguous shards of the sample indices; the launches are asynchronous (rbo_rollout_device returns after
+# the launch), so all GPUs work concurrently; rbo_get_results copies each shard of the containers back and the statistics are taken
+# over the filled containers exactly as rollout.jl:328-337. (A multi-process host all-reduces rbo_partial_sums_device instead, as
+# bench.py does with NCCL.) The rand(dim) stream is reproduced by the same two-phase scheme as on one GPU.
+const _RBO_HANDLES = RboHandle[]
+function _rbo_handles(ndev::Int)
+    while length(_RBO_HANDLES) < ndev
+        push!(_RBO_HANDLES, RboHandle(length(_RBO_HANDLES)))
+    end
+    return _RBO_HANDLES[1:ndev]
+end
+
+function simulate_trajectory_mc_multigpu(T::Trajectory, tp::TrajectoryParameters, ndev::Int;
+        inner_solve_xstarts::Matrix{Float64}, resolutions::Vector{Float64},
+        spatial_gradients_container::Matrix{Float64}, hyperparameter_gradients_container::Matrix{Float64})
+    hs = _rbo_handles(ndev)
+    fs = get_fantasy_surrogate(T)
+    set_start!(T, get_starting_point(tp))
+    N = get_known_observations(fs)
+    rn = tp.rnstream_sequence
+    M, d, hor = tp.mc_iters, length(tp.x0), tp.horizon
+    θ = Vector{Float64}(tp.θ)
+    fmini = minimum(get_observations(get_base_surrogate(T)))
+    bounds = [div(M * g, ndev) for g in 0:ndev]
+    for (g, h) in enumerate(hs)
+        _rbo_set_surrogate!(h, fs.X, fs.L.data, fs.y, fs.cs[1], N, fs.ψ, fs.g, fs.σn2)
+        _rbo_check(h, ccall((:rbo_set_normals, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cint, Cint), h.ptr, rn, M, size(rn, 3), bounds[g], bounds[g+1] - bounds[g]))
+        _rbo_check(h, ccall((:rbo_set_starts, librbo), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), h.ptr, inner_solve_xstarts, size(inner_solve_xstarts, 2)))
+    end
+    launch(h, mode, flags, dual_dev) = _rbo_check(h, ccall((:rbo_rollout_device, librbo), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+        h.ptr, tp.x0, θ, length(θ), tp.spatial_lbs, tp.spatial_ubs, hor, fmini, mode, flags, dual_dev, C_NULL, C_NULL))
+    fetch!(h, lo, hi, v, gx, gθ, bi, st) = _rbo_check(h, ccall((:rbo_get_results, librbo), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+        h.ptr, pointer(v, lo + 1), gx === nothing ? C_NULL : pointer(gx, d * lo + 1), gθ === nothing ? C_NULL : pointer(gθ, length(θ) * lo + 1),
+        bi === nothing ? C_NULL : pointer(bi, lo + 1), C_NULL, pointer(st, lo + 1)))
+    status = zeros(Int32, M); best_index = zeros(Int32, M)
+    # phase 1 on every device (values, best indices), then the reference's RNG consumption on the host, then phase 2 (replay + adjoint)
+    foreach(h -> launch(h, 0, 0, C_NULL), hs)
+    for (g, h) in enumerate(hs)
+        fetch!(h, bounds[g], bounds[g+1], resolutions, nothing, nothing, best_index, status)
+    end
+    _rbo_first_error(status)
+    dual = zeros(d, max(hor, 1), M)
+    for m in 1:M
+        t = Int(best_index[m])
+        if resolutions[m] > 0.0 && t >= 1
+            for j in t:-1:1
+                dual[:, j, m] = rand(d)
+            end
+        end
+    end
+    # rbo_rollout (host pointers) uploads the shard's dual directions; it is synchronous per handle, so phase 2 is issued through the
+    # device entry point after an explicit upload would be the asynchronous alternative -- phase 2 is ~5 % of the work (no inner solves)
+    for (g, h) in enumerate(hs)
+        lo, hi = bounds[g], bounds[g+1]
+        summary = RboSummary()
+        _rbo_check(h, ccall((:rbo_rollout, librbo), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint, Cint, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{RboSummary}),
+            h.ptr, tp.x0, θ, length(θ), tp.spatial_lbs, tp.spatial_ubs, hor, fmini, 1, 8 #= RBO_FLAG_REPLAY_TAPE =#,
+            pointer(dual, d * max(hor, 1) * lo + 1), C_NULL, pointer(resolutions, lo + 1), pointer(spatial_gradients_container, d * lo + 1),
+            pointer(hyperparameter_gradients_container, length(θ) * lo + 1), C_NULL, C_NULL, pointer(status, lo + 1), summary))
+    end
+    _rbo_first_error(status)
+    empty!(_RBO_RESIDENT)
+    μxθ = Distributions.mean(resolutions); σ_μxθ = Distributions.std(resolutions, mean = μxθ)
+    ∇μx = vec(Distributions.mean(spatial_gradients_container, dims = 2))
+    ∇μθ = vec(Distributions.mean(hyperparameter_gradients_container, dims = 2))
+    return ExpectedTrajectoryOutput(μxθ = μxθ, σ_μxθ = σ_μxθ, ∇μx = ∇μx, σ_∇μx = vec(Distributions.std(spatial_gradients_container, dims = 2, mean = ∇μx)),
+                                    ∇μθ = ∇μθ, σ_∇μθ = vec(Distributions.std(hyperparameter_gradients_container, dims = 2, mean = ∇μθ)))
+end

@@ -811,3 +811,45 @@ def test_longest_first_schedule_does_not_change_results(pkg, orc):
             eng.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert outs[0][2] >= 0.0 and outs[1][2] >= 0.0 and outs[1][2] < outs[1][3]
+
+
+def test_single_process_multi_handle_sharding(pkg, orc):
+    """What a single-process multi-GPU host (the Julia shim: one handle per device) does, emulated with three handles on device 0:
+    contiguous shards of the sample indices, asynchronous rbo_rollout_device on every handle, rbo_partial_sums_host per handle,
+    element-wise sum, rbo_finalize_sums -- against one handle that owns all samples; rbo_get_results returns each shard's slice."""
+    import ctypes as C
+    wl, sur, rn, starts, dd = setup(pkg, orc, "C2", M=90, S=6)
+    full = gpu_rollout(pkg, wl, sur, rn, starts, dd)
+    d, M, nsum = wl.d, wl.M, 1 + 3 * (1 + wl.d + 1) + 2
+    bounds = [(M * r) // 3 for r in range(4)]
+    engs, tot = [], np.zeros(nsum)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    try:
+        import torch
+        for r in range(3):
+            eng = pkg.RolloutEngine(0)
+            engs.append(eng)
+            eng.set_surrogate(pkg.FantasySurrogate(sur, wl.h)); eng.set_normals(rn, bounds[r], bounds[r + 1] - bounds[r]); eng.set_starts(starts)
+        dds = [torch.from_numpy(np.ascontiguousarray(dd[:, :, bounds[r]:bounds[r + 1]].transpose(2, 1, 0))).cuda() for r in range(3)]
+        for r, eng in enumerate(engs):   # all launches are in flight before anything is read back
+            eng.rollout_device(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), 1, dual_dirs_ptr=dds[r].data_ptr())
+        vals, gxs = [], []
+        for r, eng in enumerate(engs):
+            part = np.zeros(nsum)
+            eng.handle.check(eng.lib.rbo_partial_sums_host(eng.handle.h, p(part), nsum))
+            tot += part
+            m = bounds[r + 1] - bounds[r]
+            v, gx, st = np.zeros(m), np.zeros((d, m), order="F"), np.zeros(m, np.int32)
+            eng.handle.check(eng.lib.rbo_get_results(eng.handle.h, p(v), p(gx), None, None, None, ip(st)))
+            assert np.all(st == 0)
+            vals.append(v); gxs.append(gx)
+    finally:
+        for eng in engs:
+            eng.close()
+    assert np.array_equal(np.concatenate(vals), full["values"]) and np.array_equal(np.concatenate(gxs, axis=1), full["grad_x"])
+    mean, std = C.c_double(), C.c_double()
+    gm, gs = np.zeros(d), np.zeros(d)
+    assert pkg._lib.load().rbo_finalize_sums(p(tot), d, 1, C.byref(mean), C.byref(std), p(gm), p(gs), None, None) == 0
+    assert np.isclose(mean.value, full["values"].mean(), rtol=1e-13) and np.isclose(std.value, full["values"].std(ddof=1), rtol=1e-11)
+    assert np.allclose(gm, full["grad_x"].mean(axis=1), rtol=1e-12) and np.allclose(gs, full["grad_x"].std(axis=1, ddof=1), rtol=1e-10)
