@@ -522,10 +522,10 @@ void tri_solve_neg(const double* ta, const double* te, const double* b, int n, d
 // shifts S = {lam >= 0 : T + lam I positive definite and |h(lam)| <= Delta} form a half-line [lam*, inf): lam* = 0 is the
 // interior Newton step (optim.jl:13-21), otherwise the boundary solution, and in the hard case lam* = -lambda_min with
 // |h(lam*)| < Delta, completed along the lowest eigenvector (optim.jl:39-46). lam* is located by TR_ROUNDS rounds of
-// TR_CAND-way multisection (each lane of the CUDA warp tests two candidates), i.e. to 1/(63 * 64^3) = 6e-8 of the initial
+// TR_CAND-way multisection (each lane of the CUDA warp tests two candidates), i.e. to 1/(63 * 64^2) = 4e-6 of the initial
 // bracket: a trust-region step does not need |p| = Delta to more than that. Hff: n x n row-major (overwritten).
 // Returns true when the constraint is active ("hit_constraint").
-constexpr int TR_ROUNDS = 4, TR_CAND = 64;
+constexpr int TR_ROUNDS = 3, TR_CAND = 64;
 bool tr_step(double* Hff, const double* gf, int n, double Delta, double* pout, double* work /* >= 8 n */) {
   double* ta = work; double* te = ta + n; double* beta = te + n; double* gt = beta + 2 * n; double* wk = gt + n;  // wk: 2n
   if (n == 1) {

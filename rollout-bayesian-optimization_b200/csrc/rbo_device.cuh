@@ -17,7 +17,7 @@
 #define RBO_LP 36        // doubles per k in a packed L0 panel: 32 rows + 4 pad (288-byte pitch)
 #define RBO_CHUNK_K 32   // k-values per staged panel chunk (32 * 288 B = 9216 B per bulk copy); == RBO_BR
 #define RBO_NSTAGE 3     // stages of the panel ring buffer
-#define RBO_TR_ROUNDS 4  // rounds of 64-way multisection for the trust-region shift (oracle: TR_ROUNDS, TR_CAND)
+#define RBO_TR_ROUNDS 3  // rounds of 64-way multisection for the trust-region shift (oracle: TR_ROUNDS, TR_CAND)
 #define RBO_FLAG_MYOPIC_INTERNAL (1 << 16)  // kernel-internal: myopic multistart against the base surrogate
 
 namespace rbo {
