@@ -31,6 +31,11 @@ def main(name="C3", M=296, large_n=False):
     fa = getattr(eng.lib, "rbo_debug_aux_cycles" + sfx)
     fa.argtypes = fn.argtypes
     fa(eng.handle.h, aux, 1)
+    ft = getattr(eng.lib, "rbo_debug_tr_cycles" + sfx, None)
+    trc = (ctypes.c_ulonglong * 16)()
+    if ft is not None:
+        ft.argtypes = fn.argtypes
+        ft(eng.handle.h, trc, 1)
     s = eng.rollout(wl.x0, wl.theta, wl.lbs, wl.ubs, wl.h, float(np.min(sur.y)), vals, gx, gt, dual_dirs=dd)
     fn(eng.handle.h, out, 1)
     tot = sum(out[i] for i in range(12))
@@ -43,6 +48,14 @@ def main(name="C3", M=296, large_n=False):
     tot_calls = sum(aux[i] for i in range(16))
     print("  per-start solver step (slot_logic_warp) duration histogram, bins of 4k cycles (last bin: >= 60k): " +
           " ".join(f"{100 * aux[i] / max(tot_calls, 1):.1f}%" for i in range(16)))
+    if ft is not None:
+        ft(eng.handle.h, trc, 0)
+        calls = max(trc[0], 1)
+        names = ["calls", "state machine before the step", "trust-region step", "after the step (projection, predicted decrease)", "  tr: load", "  tr: Householder",
+                 "  tr: write-out + Gershgorin", "  tr: multisection probes", "  tr: tridiagonal solve (+ hard case)", "  tr: back-transformation"]
+        print(f"  per-start logic by part (n <= 16 path), cycles per trust-region step over {trc[0]} steps:")
+        for i in range(1, 10):
+            print(f"    {names[i]:<52} {trc[i] / calls:9.0f}")
     eng.close()
 
 if __name__ == "__main__":
