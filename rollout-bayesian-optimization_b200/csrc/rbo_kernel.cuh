@@ -12,6 +12,7 @@ struct SmemPlan {
   int sf, slam, spred, shs, ssn;             // per slot scalars: merit f, trust-region radius, predicted decrease, alpha, |step|_2
   int ppre, ppost, phess;                    // partial sums of the row reductions
   int bestx, misc, adj;                      // [d] best candidate ; scalar/scratch area ; adjoint duals
+  int sbnd;                                  // [2][d] box bounds (lane-indexed reads: kernel parameters would be serialised constant loads)
   int pairs, tbl, ints;                      // int areas (in doubles)
   int total;                                 // total doubles
 };
@@ -110,6 +111,7 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.bestx = take(d);
   p.misc = take(64 + 2 * q1 * q1 + 2 * q1);
   p.adj = take(19 * d + 32);
+  p.sbnd = take(2 * d);
   p.pairs = take((6 * (W + 2) + 1) / 2);  // product items
   p.tbl = take((T2 + 2) / 2 + 1);
   p.ints = take(64 + 10 * W + 32 * W / 2 + (ncols_adjoint(d) + W * q1 + 1) / 2);

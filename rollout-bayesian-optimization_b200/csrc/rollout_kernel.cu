@@ -86,6 +86,14 @@ __device__ __forceinline__ double warp_min(double v) {
   for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, off));
   return v;
 }
+// max over the warp of a value that is >= 0 in every lane: the IEEE bit pattern of non-negative doubles is monotone, so two integer
+// REDUX instructions replace five shuffle rounds (a shuffle costs ~45 cycles of latency on B200)
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(FULL, hi);
+  const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
+}
 // index of (p, q), p <= q, in the row-major upper triangle of an n x n matrix
 __device__ __forceinline__ int tri_idx(int p, int q, int n) { return p * n - (p * (p - 1)) / 2 + (q - p); }
 
@@ -431,8 +439,23 @@ __device__ __noinline__ bool tr_step16(const double* H, const double* g, const i
     const int j = c0 + c;
     if (row == j && rin) ta[row] = a[c];
     if (row == j + 1 && rin) te[j] = a[c];
-    const double yj = rowsum16(Q[c] * gi);  // (Q'g)_j
-    if (row == 0 && j < n) yv[j] = yj;
+  }
+  {
+    // (Q'g)_j = sum over the rows of Q[row][j] g_row as a reduce-scatter: every round halves the columns a lane keeps and doubles
+    // the rows they cover (8 double shuffles instead of 32); the lane ends with column c0 + 4 b4 + 2 b3 + b2 (bK = bit K of the lane)
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+    double k4[4], k2[2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double lo_ = Q[c] * gi, hi_ = Q[c + 4] * gi;
+      k4[c] = (b4 ? hi_ : lo_) + __shfl_xor_sync(FULL, b4 ? lo_ : hi_, 16);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) k2[c] = (b3 ? k4[c + 2] : k4[c]) + __shfl_xor_sync(FULL, b3 ? k4[c] : k4[c + 2], 8);
+    double k1 = (b2 ? k2[1] : k2[0]) + __shfl_xor_sync(FULL, b2 ? k2[0] : k2[1], 4);
+    k1 += __shfl_xor_sync(FULL, k1, 2);
+    const int j = c0 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+    if ((lane & 2) == 0 && j < n) yv[j] = k1;
   }
   __syncwarp();
   const bool in = lane < n;
@@ -1362,15 +1385,21 @@ RBO_ROW_UNROLL
       __syncwarp();
       return keep;
     };
-    auto accept_state = [&]() {  // (x, alpha, f, g, H) <- trial evaluation, in the merit's variables
+    const double* lb = sm + pl.sbnd; const double* ub = lb + d;
+    const int T2 = d * (d + 1) / 2;
+    auto accept_state = [&](double fnew) {  // (x, alpha, f, g, H) <- trial evaluation, in the merit's variables; fnew = merit at the trial point
       alpha = at;
+      f = fnew;
       if (flg & 1) {
         const double ia = 1.0 / at;
-        f = -log(at);
         for (int a = lane; a < d; a += 32) { x[a] = xt[a]; g[a] = -ga[a] * ia; }
-        for (int i = lane; i < dd; i += 32) { const int a = i / d, b = i - a * d; H[i] = Ht[i] * ia + (ga[a] * ia) * (ga[b] * ia); }
+        __syncwarp();
+        for (int e = lane; e < T2; e += 32) {  // H = Ht / alpha + (ga / alpha)(ga / alpha)', both triangles
+          const int pq = tbld[e], p = pq & 0xff, q = pq >> 8;
+          const double hv = Ht[p * d + q] * ia + g[p] * g[q];
+          H[p * d + q] = hv; H[q * d + p] = hv;
+        }
       } else {
-        f = -at;
         for (int a = lane; a < d; a += 32) { x[a] = xt[a]; g[a] = -ga[a]; }
         for (int i = lane; i < dd; i += 32) H[i] = Ht[i];
       }
@@ -1385,7 +1414,7 @@ RBO_ROW_UNROLL
         return store(RBO_SOLVE_NAN, false);
       }
       flg = (P.rule_id != RBO_RULE_LCB && at > 0.0) ? 1 : 0;
-      accept_state();
+      accept_state((flg & 1) ? -log(at) : -at);
       if (single) return store(RBO_SOLVE_CONVERGED, false);  // one evaluation at a given point (extended tape): no iteration
       double wmax = 0.0;
       for (int a = 0; a < d; ++a) wmax = fmax(wmax, P.ubs[a] - P.lbs[a]);
@@ -1397,7 +1426,7 @@ RBO_ROW_UNROLL
       const double ft = fin ? ((flg & 1) ? -log(at) : -at) : 0.0;
       const double rho = fin ? (f - ft) / pred : -1.0;
       if (fin && rho >= o.eta) {  // optim.jl:99
-        accept_state();
+        accept_state(ft);
         if (rho > 0.75 && (flg & 2) && sn >= 0.8 * Delta) {  // optim.jl:95-96
           double dm2 = 0.0;
           for (int a = 0; a < d; ++a) { const double wd = P.ubs[a] - P.lbs[a]; dm2 = fma(wd, wd, dm2); }
@@ -1417,17 +1446,18 @@ RBO_ROW_UNROLL
     // active set (lane a <-> coordinate a) and projected gradient of alpha
     const bool in = lane < d;
     const double xa = in ? x[lane] : 0.0, gg = in ? g[lane] : 0.0;
-    const bool act = in && ((xa <= P.lbs[lane] && gg > 0.0) || (xa >= P.ubs[lane] && gg < 0.0));
-    const unsigned fmask = __ballot_sync(FULL, in && !act);
-    const int nfree = __popc(fmask);
+    const double lba = in ? lb[lane] : 0.0, uba = in ? ub[lane] : 0.0;
+    const bool act = in && ((xa <= lba && gg > 0.0) || (xa >= uba && gg < 0.0));
     const bool isfree = in && !act;
-    double pg = warp_max(isfree ? fabs(gg) : 0.0);
+    const unsigned fmask = __ballot_sync(FULL, isfree);
+    const int nfree = __popc(fmask);
+    if (isfree) fr[__popc(fmask & ((1u << lane) - 1u))] = lane;  // free coordinates in ascending order
+    double pg = warp_max_nonneg(isfree ? fabs(gg) : 0.0);
     if (flg & 1) pg *= alpha;
-    if (lane < nfree) fr[lane] = __fns(fmask, 0, lane + 1);
     __syncwarp();
     if (fresh && pg <= o.gtol * fmax(1.0, fabs(alpha))) return store(RBO_SOLVE_CONVERGED, false);
     const int myc = lane < nfree ? fr[lane] : 0;  // coordinate owned by this lane in the reduced system
-    const double xmax = warp_max(fabs(xa));
+    const double xmax = warp_max_nonneg(fabs(xa));
     for (;;) {
       double* yv = sm + pl.sdmu + sl * d;  // grad mu / grad sigma / grad alpha of the evaluation are not needed any more: scratch
       TR_T(l1_); TR_ADD(1, l0_, l1_); TR_ADD(0, 0, 1);
@@ -1435,17 +1465,36 @@ RBO_ROW_UNROLL
                                                   : tr_step_warp(H, g, fr, nfree, d, Delta, A, yv);
       const double t = lane < nfree ? yv[lane] : 0.0;
       TR_T(l2_); TR_ADD(2, l1_, l2_);
-      for (int a = lane; a < d; a += 32) xt[a] = x[a];
+      if (in) xt[lane] = xa;
       __syncwarp();
-      if (lane < nfree) xt[myc] = fmin(fmax(x[myc] + t, P.lbs[myc]), P.ubs[myc]);
+      if (lane < nfree) xt[myc] = fmin(fmax(x[myc] + t, lb[myc]), ub[myc]);
       __syncwarp();
       const double sa = in ? xt[lane] - xa : 0.0;
-      const double smax = warp_max(fabs(sa));
-      sn = sqrt(warp_sum(sa * sa));
-      if (smax <= o.xtol * fmax(1.0, xmax)) return store(RBO_SOLVE_STEP_TINY, false);
+      const double smax = warp_max_nonneg(fabs(sa));
+      if (smax <= o.xtol * fmax(1.0, xmax)) { sn = sqrt(warp_sum(sa * sa)); return store(RBO_SOLVE_STEP_TINY, false); }
+      // H s: the step goes to shared memory (the scratch is free again), then lane a walks row a of H
+      if (in) yv[lane] = sa;
+      __syncwarp();
       double hsv = 0.0;
-      if (in) for (int b = 0; b < d; ++b) hsv = fma(H[lane * d + b], xt[b] - x[b], hsv);
-      const double gs = warp_sum(gg * sa), sHs = warp_sum(sa * hsv);
+      if (in) {
+        const double* Hr = H + lane * d;
+        if ((d & 1) == 0) {  // rows and the scratch are 16-byte aligned: two entries per load
+          double h1 = 0.0;
+          for (int b = 0; b < d; b += 2) {
+            const double2 hh = *reinterpret_cast<const double2*>(Hr + b), ss = *reinterpret_cast<const double2*>(yv + b);
+            hsv = fma(hh.x, ss.x, hsv); h1 = fma(hh.y, ss.y, h1);
+          }
+          hsv += h1;
+        } else for (int b = 0; b < d; ++b) hsv = fma(Hr[b], yv[b], hsv);
+      }
+      // |s|^2, g's, s'Hs in the same shuffle rounds
+      double r0 = sa * sa, r1 = gg * sa, r2 = sa * hsv;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        r0 += __shfl_xor_sync(FULL, r0, off); r1 += __shfl_xor_sync(FULL, r1, off); r2 += __shfl_xor_sync(FULL, r2, off);
+      }
+      sn = sqrt(r0);
+      const double gs = r1, sHs = r2;
       const double pr = -(gs + 0.5 * sHs);  // mu_diff of optim.jl:88 for the projected step
       if (!(pr > 0.0)) {
         Delta = 0.25 * fmin(Delta, sn);
@@ -1529,10 +1578,19 @@ RBO_ROW_UNROLL
       hess_sums<3>(nact, pt, cb, cb, RShw);
       __syncthreads();
       PT_MARK(5);
+      // the row-split partial sums are added (fixed order) by all threads, in place: the per-start warps then read one value per
+      // entry instead of RS -- their time is what the other eleven warps wait for
+      {
+        const int n1 = nact * q1 * q2, nh = nact * 2 * (d * (d + 1) / 2 + 1);
+        double* pp = sm + pl.ppost; double* ph = sm + pl.phess;
+        if (RS1 > 1) for (int i = tid; i < n1; i += RBO_THREADS) { double a_ = pp[i]; for (int r = 1; r < RS1; ++r) a_ += pp[(size_t)r * n1 + i]; pp[i] = a_; }
+        if (RShw > 1) for (int i = tid; i < nh; i += RBO_THREADS) { double a_ = ph[i]; for (int r = 1; r < RShw; ++r) a_ += ph[(size_t)r * nh + i]; ph[i] = a_; }
+        __syncthreads();
+      }
       // per-start logic: one warp per active slot
       for (int s = warp; s < nact; s += RBO_NWARPS) {
         const int sl = alist[s];
-        assemble_warp(sl, s, nact, -q2, sm + pl.ppost + s * q1 * q2, nact * q1 * q2, RS1, sm + pl.ppost, nact * q1 * q2, s * q1 * q2 + q2 + 1, q2, RSg, RShc, RShw, misc[1], single ? sm + pl.sHref : nullptr);
+        assemble_warp(sl, s, nact, -q2, sm + pl.ppost + s * q1 * q2, nact * q1 * q2, 1, sm + pl.ppost, nact * q1 * q2, s * q1 * q2 + q2 + 1, q2, 1, 1, 1, misc[1], single ? sm + pl.sHref : nullptr);
 #ifdef RBO_PHASE_TIMERS
         long long ta_ = clock64();
         if (tid == 0) atomicAdd(&g_phase_cycles[8], (unsigned long long)(ta_ - pt_t0));
@@ -1592,6 +1650,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) RBO_KERNEL_NAME(const __grid_c
   double* misc = k.misc;  // misc[0] best f, misc[1] fstar, misc[2..7] scalars, misc[8..] scratch
   int* si = k.si;
   k.build_tables();
+  for (int i = tid; i < 2 * d; i += RBO_THREADS) smem[P.pl.sbnd + i] = i < d ? P.lbs[i] : P.ubs[i - d];
   k.pipe_init();
   for (int i = tid; i < NR * RP; i += RBO_THREADS) k.V[i] = 0.0;  // rows beyond the fantasy block are read (times exact zeros of L0's padding) but never written
   if (P.xsm) for (int i = tid; i < d * N8; i += RBO_THREADS) k.Xs[(i / N8) * P.XP + (i % N8)] = __ldg(P.Xb + i);
