@@ -234,6 +234,12 @@ int rbo_multistart_base_solve(rbo_handle* h, const double* theta, int ntheta, co
 /* Dense FP64 FMA micro-benchmark on this handle's device (TFLOP/s): the roofline denominator of this path,
  * because MEASURED_PEAKS.json carries no FP64 figure. */
 int rbo_fp64_peak(rbo_handle* h, double* tflops);
+/* Diagnostic: the device code of the inner solver's exact trust-region step (replaces the subproblem solves
+ * inside Optim.IPNewton, rbf_optim.jl:24-30, and follows solve_tr, optim.jl:9-51) on B independent subproblems
+ * min g'p + p'Hp/2, |p|_2 <= Delta: H[B][n*n] (symmetric, row-major), g[B][n], Delta[B] -> p[B][n], hit[B] (1: constraint
+ * active). 2 <= n <= 16 takes the register-resident path of the rollout kernel, other n the general one. For step-level parity
+ * tests against the oracle's orc_tr_step. */
+int rbo_tr_step_batch(rbo_handle* h, int n, int B, const double* H, const double* g, const double* Delta, double* p, int* hit);
 /* Number of SMs of the handle's device. */
 int rbo_num_sms(const rbo_handle* h);
 

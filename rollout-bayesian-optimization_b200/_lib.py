@@ -61,6 +61,7 @@ SYMBOLS = {
     "rbo_generate_initial_guesses": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]),
     "rbo_multistart_base_solve": (C.c_int, [C.c_void_p, _dp, C.c_int, _dp, _dp, _dp, _dp, C.POINTER(Summary)]),
     "rbo_fp64_peak": (C.c_int, [C.c_void_p, _dp]),
+    "rbo_tr_step_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _ip]),
     "rbo_num_sms": (C.c_int, [C.c_void_p]),
 }
 

@@ -555,6 +555,18 @@ class RolloutEngine:
     def num_sms(self):
         return self.lib.rbo_num_sms(self.handle.h)
 
+    def tr_step_batch(self, H, g, Delta):
+        """Diagnostic: the kernel's exact trust-region step on B subproblems: H [B, n, n], g [B, n], Delta [B]
+        -> (p [B, n], hit [B]); the counterpart of the oracle's tr_step."""
+        H = np.ascontiguousarray(H, dtype=np.float64); g = np.ascontiguousarray(g, dtype=np.float64)
+        Delta = np.ascontiguousarray(Delta, dtype=np.float64)
+        B, n = g.shape
+        if H.shape != (B, n, n) or Delta.shape != (B,):
+            raise ValueError("tr_step_batch: H must be [B, n, n], g [B, n], Delta [B]")
+        p = np.zeros((B, n)); hit = np.zeros(B, np.int32)
+        self.handle.check(self.lib.rbo_tr_step_batch(self.handle.h, n, B, dptr(H), dptr(g), dptr(Delta), dptr(p), iptr(hit)))
+        return p, hit.astype(bool)
+
 
 def _mean_std_rows(A):
     """rollout.jl:328-337: Distributions.mean / std(..., mean=) -- corrected sample std per row."""

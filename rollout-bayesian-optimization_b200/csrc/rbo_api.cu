@@ -22,6 +22,7 @@ __global__ void rbo_sobol_kernel(const unsigned* dirs, unsigned* out_u32, double
 __global__ void rbo_stats_kernel(const double* values, const double* gx, const double* gth, const int* n_evals, const int* best_index, const int* grad_case,
                                  const int* status, int M, int d, int nth, int h, double* sums);
 __global__ void rbo_fp64_peak_kernel(double* out, int iters);
+__global__ void rbo_tr_step_kernel(const double* H, const double* g, const double* Delta, int n, int B, double* p, int* hit);
 __global__ void rbo_gather_sums_kernel(const double* sums, int need, int idx_failed, const int* work_counter, double* out);
 __global__ void rbo_lpt_order_kernel(const int* n_evals, const int* grad_case, const int* best_index, int M, int hh, int* order);
 // surrogate_kernels.cu
@@ -939,6 +940,27 @@ int rbo_fp64_peak(rbo_handle* h, double* tflops) {
     if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
   }
   *tflops = best;
+  return RBO_SUCCESS;
+}
+
+int rbo_tr_step_batch(rbo_handle* h, int n, int B, const double* H, const double* g, const double* Delta, double* p, int* hit) {
+  if (!h || !H || !g || !Delta || !p || !hit || B < 1) return RBO_ERR_ARG;
+  if (n < 1 || n > RBO_MAXD) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_tr_step_batch: n = %d outside [1, %d]", n, RBO_MAXD);
+  CK(h, cudaSetDevice(h->device));
+  double *dH = nullptr, *dg = nullptr, *dD = nullptr, *dp = nullptr; int* dh = nullptr;
+  struct Guard { void** p[5]; ~Guard() { for (auto q : p) if (*q) cudaFree(*q); } } guard{{(void**)&dH, (void**)&dg, (void**)&dD, (void**)&dp, (void**)&dh}};
+  CK(h, cudaMalloc((void**)&dH, (size_t)B * n * n * 8)); CK(h, cudaMalloc((void**)&dg, (size_t)B * n * 8)); CK(h, cudaMalloc((void**)&dD, (size_t)B * 8));
+  CK(h, cudaMalloc((void**)&dp, (size_t)B * n * 8)); CK(h, cudaMalloc((void**)&dh, (size_t)B * 4));
+  CK(h, cudaMemcpyAsync(dH, H, (size_t)B * n * n * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(dg, g, (size_t)B * n * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(dD, Delta, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
+  const int wpb = n > 16 ? 2 : 4;  // <= 48 KB of dynamic shared memory
+  const size_t smem = (size_t)wpb * (2 * n * n + 4 * n + 32) * 8;
+  rbo_tr_step_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, smem, h->stream>>>(dH, dg, dD, n, B, dp, dh);
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(p, dp, (size_t)B * n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(hit, dh, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
   return RBO_SUCCESS;
 }
 

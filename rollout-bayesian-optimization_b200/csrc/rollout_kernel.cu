@@ -6,13 +6,14 @@
 //   * keeps the trajectory's state in shared memory: the (<= 8) fantasy rows of the Cholesky factor as one
 //     8-row panel, the coefficient tape cs[0..h+1], u = L^-1 y, fantasy locations / draws;
 //   * every surrogate evaluation is expressed as column operations on a shared-memory matrix V (rows =
-//     observations, columns = right-hand sides): build kernel columns, triangular solves against
-//     [L0 (global, pre-packed 8-row panels with inverted 8x8 diagonal blocks, read through L1/L2) ; fantasy panel],
-//     then row reductions (dot products of column pairs; lanes walk the rows, warps own blocks of pairs);
+//     observations, columns = right-hand sides): build kernel columns, "triangular solves" as panel products with the
+//     EXPLICIT inverse of the base factor (32-row panels streamed once per pass by a TMA producer warp through a
+//     3-stage shared-memory ring, FP64 tensor-core MMA by the consumer warps) followed by the <= 8 fantasy rows,
+//     then row reductions (A'B products of column blocks on the tensor cores, fixed-order row splits);
 //   * the multi-start inner solve (replacing rbf_optim.jl:68-101 / Optim.IPNewton) keeps W start slots busy in
 //     lock-step rounds: each round evaluates (alpha, grad alpha, Hess alpha) at one trial point per active slot,
-//     one warp per slot then runs the regularised projected Newton logic, finished slots are refilled from the
-//     start queue;
+//     one warp per slot then runs one step of the exact trust-region Newton method (the n <= 16
+//     subproblem entirely in registers, tr_step16), finished slots are refilled from the start queue;
 //   * the adjoint (rollout.jl:233-277) replays the tape: each policy solve i = t..1 is re-evaluated ONCE and its
 //     perturbation columns (rbs.jl:633-764) are pushed into the right-hand sides of the earlier duals.
 //
@@ -424,7 +425,11 @@ __device__ __noinline__ bool tr_step16(const double* H, const double* g, const i
       const double pv = ql + __shfl_xor_sync(FULL, ql, 1);
       const double nkk = -0.5 * bk * pv, wi = fma(nkk, vi, pw);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) { const double wj = fma(nkk, v[c], w[c]); a[c] = fma(-vi, wj, a[c]); a[c] = fma(-wi, v[c], a[c]); }
+      // The update must keep A BITWISE symmetric (the reflector column is read from row k): v_i w_j + w_i v_j is formed from two
+      // rounded products and one commutative addition, never contracted into FMAs. With a merely approximately symmetric A the
+      // two copies of a rounding-noise column differ by O(1) relative and the transformation stops being a similarity -- that
+      // corrupted the near-zero eigenvalues of rank-deficient Hessians (tests: test_trust_region_step_matches_the_oracle_step).
+      for (int c = 0; c < 8; ++c) { const double wj = fma(nkk, v[c], w[c]); a[c] = __dsub_rn(a[c], __dadd_rn(__dmul_rn(vi, wj), __dmul_rn(wi, v[c]))); }
       if (lane == 2 * (k + 1) + (k >> 3)) a[k & 7] = alpha;                       // sub-diagonal of T
       // Q <- Q (I - beta v v'): off the critical path
       const double tq = bk * fma(-qk1, alpha, uraw);
@@ -2231,6 +2236,24 @@ __global__ void rbo_gather_sums_kernel(const double* __restrict__ sums, int need
 }
 
 // FP64 FMA micro-benchmark: the roofline denominator for this path (MEASURED_PEAKS.json has no FP64 figure).
+// Diagnostic (rbo_tr_step_batch): the device code of the per-start trust-region step on B independent subproblems, one warp each,
+// through the same dispatch as slot_logic_warp (registers for 2 <= n <= 16, shared memory otherwise). H: [B][n*n], g: [B][n],
+// p: [B][n], hit: [B].
+__global__ void rbo_tr_step_kernel(const double* H, const double* g, const double* Delta, int n, int B, double* p, int* hit) {
+  extern __shared__ __align__(16) double trs[];
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, w = threadIdx.x >> 5, b = blockIdx.x * wpb + w;
+  if (b >= B) return;
+  double* base = trs + (size_t)w * (2 * n * n + 4 * n + 32);
+  double* Hs = base; double* A = Hs + n * n; double* gs = A + n * n; double* ta = gs + n; double* te = ta + n; double* yv = te + n;
+  int* fr = reinterpret_cast<int*>(yv + n);
+  for (int i = lane; i < n * n; i += 32) Hs[i] = H[(size_t)b * n * n + i];
+  if (lane < n) { gs[lane] = g[(size_t)b * n + lane]; fr[lane] = lane; }
+  __syncwarp();
+  const bool h_ = (n >= 2 && n <= 16) ? tr_step16(Hs, gs, fr, n, n, Delta[b], ta, te, yv) : tr_step_warp(Hs, gs, fr, n, n, Delta[b], A, yv);
+  if (lane < n) p[(size_t)b * n + lane] = yv[lane];
+  if (lane == 0) hit[b] = h_ ? 1 : 0;
+}
+
 __global__ void rbo_fp64_peak_kernel(double* out, int iters) {
   double a[16];
 #pragma unroll
