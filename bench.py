@@ -36,7 +36,7 @@ import __graft_entry__ as graft  # noqa: E402
 METRIC = "rollout trajectories/sec (value+grad)"
 UNIT = "trajectories/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the rollout kernel (ncu --set full, 1 GPU, default M): (bytes, capture)
-TRAFFIC_NCU = {"C3": (15742464, "profiles/r1f_dram_fullM.csv")}
+TRAFFIC_NCU = {"C3": (15552768, "profiles/r3_dram_c3_fullM.csv")}
 
 
 def parse():
@@ -394,7 +394,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
                 "steps": e2e_steps, "all_trajectories_ok": ok_e2e, "host_breakdown_ms": brk},
-        "gpu_launches": 3 * args.steps,  # rollout kernel + statistics + partial-sums gather per step
+        "gpu_launches": 4 * args.steps,  # per step: rollout kernel + statistics + longest-first order for the next launch + partial-sums gather
         "roofline": {"bound": "tensor", "pipe": "FP64 (mma.sync.m8n8k4.f64 and DFMA share the same 64 FMA/clk/SM)", "achieved": achieved_per_gpu, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_per_gpu / peak_tf,
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload (1 GPU), from the ncu
                      # capture named in traffic_source

@@ -508,14 +508,14 @@ static bool choose_plan(const rbo_handle* h, int hor, int S, int mode, PlanChoic
     int RP = std::max(W * CS, nadj) + 2;
     if ((RP & 1) == 0) RP += 1;  // odd pitch: conflict-free column walks
     int NPmax = npairs_max(d, W);
-    SmemPlan pl = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm, RSmax, vglob);
+    SmemPlan pl = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm, RSmax, vglob, S);
     size_t bytes = (size_t)pl.total * 8;
     if (bytes > (size_t)h->max_smem) return false;
     *pc = {W, RP, NR, RSmax, NPmax, xsm, bytes, RSmax, vglob};
     // the Hessian sums are tensor-pipe bound per scheduler: give them enough row splits to occupy every warp if that still fits
     const int want = std::min(4, std::max(RSmax, RBO_NWARPS / W));
     for (int rsh = want; rsh > RSmax; --rsh) {
-      SmemPlan p2 = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm, rsh, vglob);
+      SmemPlan p2 = make_plan(d, N8, hor, W, RP, NR, RSmax, NPmax, xsm, rsh, vglob, S);
       if ((size_t)p2.total * 8 <= (size_t)h->max_smem) { pc->RSh = rsh; pc->bytes = (size_t)p2.total * 8; break; }
     }
     return true;
@@ -582,7 +582,7 @@ static int launch_rollout(rbo_handle* h, const double* x0, const double* theta, 
   memset(&P, 0, sizeof(P));
   P.d = h->d; P.N = h->N; P.N8 = h->N8; P.nb8 = h->nb8; P.nb32 = h->nb32; P.h = horizon; P.S = S; P.W = pc.W; P.RSmax = pc.RSmax; P.NPmax = pc.NPmax; P.xsm = pc.xsm; P.XP = h->N8 + 1;
   P.RSh = pc.RSh;
-  P.pl = make_plan(P.d, P.N8, horizon, pc.W, pc.RP, pc.NR, pc.RSmax, pc.NPmax, pc.xsm, pc.RSh, pc.vglob);
+  P.pl = make_plan(P.d, P.N8, horizon, pc.W, pc.RP, pc.NR, pc.RSmax, pc.NPmax, pc.xsm, pc.RSh, pc.vglob, S);
   P.vglob = pc.vglob;
   P.CS = h->d + 3; P.RP = pc.RP; P.NR = pc.NR; P.M = M; P.Ms = Ms; P.B = std::max(B, 1); P.x0_batch = (B > 1 || x0_batch_dev) ? x0_batch_dev : nullptr; P.hp1 = h->hp1; P.mode = mode; P.flags = flags; P.ntheta = ntheta;
   P.kern = h->kern; P.rule_id = h->rule_id; P.sigma_tol = h->sigma_tol; P.sigma_n2 = h->sigma_n2; P.k0 = h->k0; P.d2k0 = h->d2k0;

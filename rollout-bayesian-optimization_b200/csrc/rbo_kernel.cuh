@@ -12,6 +12,7 @@ struct SmemPlan {
   int sf, slam, spred, shs, ssn;             // per slot scalars: merit f, trust-region radius, predicted decrease, alpha, |step|_2
   int ppre, ppost, phess;                    // partial sums of the row reductions
   int bestx, misc, adj;                      // [d] best candidate ; scalar/scratch area ; adjoint duals
+  int sord;                                  // [3][S] uint16: evaluations of every start in the previous multistart / in the first multistart of the previous trajectory; order in which the starts are handed out
   int sbnd;                                  // [2][d] box bounds (lane-indexed reads: kernel parameters would be serialised constant loads)
   int pairs, tbl, ints;                      // int areas (in doubles)
   int total;                                 // total doubles
@@ -87,7 +88,7 @@ __host__ __device__ inline int npairs_max(int d, int W) {
   return a > b ? a : b;
 }
 
-__host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int RP, int NR, int RSmax, int NPmax, int xsm, int RSh, int vglob = 0) {
+__host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int RP, int NR, int RSmax, int NPmax, int xsm, int RSh, int vglob = 0, int S = 0) {
   SmemPlan p;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };  // keep 16-byte alignment
@@ -112,6 +113,7 @@ __host__ __device__ inline SmemPlan make_plan(int d, int N8, int h, int W, int R
   p.misc = take(64 + 2 * q1 * q1 + 2 * q1);
   p.adj = take(19 * d + 32);
   p.sbnd = take(2 * d);
+  p.sord = take((6 * S + 7) / 8);
   p.pairs = take((6 * (W + 2) + 1) / 2);  // product items
   p.tbl = take((T2 + 2) / 2 + 1);
   p.ints = take(64 + 10 * W + 32 * W / 2 + (ncols_adjoint(d) + W * q1 + 1) / 2);

@@ -728,6 +728,7 @@ struct K {
   unsigned long long* mbar;
   unsigned qglob;  // running count of staged panel chunks (ring position and mbarrier parity)
   int *alist, *phase, *sstat, *siter, *stry, *sstart, *sevals, *sflag, *sfr, *colidx, *items, *tbld;
+  unsigned short *evprev, *evfirst, *sorder;  // [S] evaluations of every start in the previous multistart of this CTA / in the first multistart of its previous trajectory; hand-out order of the starts
 
   __device__ K(const DevProblem& P_, double* sm_) : P(P_), pl(P_.pl), sm(sm_) {
     tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
@@ -745,6 +746,7 @@ struct K {
     si = reinterpret_cast<int*>(sm + pl.ints);
     items = reinterpret_cast<int*>(sm + pl.pairs);
     tbld = reinterpret_cast<int*>(sm + pl.tbl);
+    evprev = reinterpret_cast<unsigned short*>(sm + pl.sord); evfirst = evprev + P.S; sorder = evfirst + P.S;
     const int W = P.W;
     alist = si + I_ARR; phase = alist + W; sstat = phase + W; siter = sstat + W; stry = siter + W;
     sstart = stry + W; sevals = sstart + W; sflag = sevals + W; sfr = sflag + W; colidx = sfr + 32 * W;
@@ -1539,13 +1541,27 @@ RBO_ROW_UNROLL
   // ------------------------------------------------------------------------------------------------
   // single = true: ONE evaluation at `bestx` through slot 0 (no clamping, no start list): afterwards slot 0 holds mu, sigma, alpha,
   // grad mu, grad sigma and the reference's H alpha there (the extended tape of the step-level parity tests).
-  __device__ void multistart(size_t tape_off, bool single = false) {
+  __device__ void multistart(size_t tape_off, bool single = false, bool first = false) {
     const int d = P.d, W = P.W, q1 = d + 1;
+    __syncthreads();
+    // Longest first: the starts are handed out in descending order of the evaluations they needed in the previous multistart of
+    // this CTA (the same start points, a surrogate that differs by one fantasy observation) -- for the first step of a trajectory:
+    // in the first step of the CTA's previous trajectory (ties and the very first multistart: start order). With 8+2 starts on
+    // 5 slots the lock-step rounds end when the slowest start ends; one start of C3 systematically needs 15 evaluations against a
+    // mean of 8 -- begun in the first wave instead of the second it no longer sets the tail (rounds per trajectory 124 -> 105).
+    // The result does not depend on the order: the argmin compares (value, start index).
+    const unsigned short* evsrc = first ? evfirst : evprev;
+    for (int i = tid; i < P.S; i += RBO_THREADS) {
+      const unsigned e = evsrc[i];
+      int r = 0;
+      for (int j = 0; j < P.S; ++j) { const unsigned ej = evsrc[j]; r += (ej > e || (ej == e && j < i)) ? 1 : 0; }
+      sorder[r] = (unsigned short)i;
+    }
     __syncthreads();
     if (tid == 0) {
       si[I_BEST] = -1; si[I_EVALS] = 0; misc[0] = 0.0;
       const int n0 = single ? 1 : min(W, P.S);
-      for (int i = 0; i < n0; ++i) { alist[i] = i; load_start(i, i); }
+      for (int i = 0; i < n0; ++i) { alist[i] = i; load_start(i, single ? i : (int)sorder[i]); }
       if (single) for (int a = 0; a < d; ++a) (sm + pl.sxt)[a] = bestx[a];
       si[I_NACT] = n0; si[I_NEXT] = single ? P.S : n0;
     }
@@ -1620,13 +1636,14 @@ RBO_ROW_UNROLL
           bool bad = !isfinite(f);
           for (int a = 0; a < d; ++a) bad = bad || isnan(x[a]);
           si[I_EVALS] += sevals[sl];
+          if (!single) { evprev[sid] = (unsigned short)min(sevals[sl], 65535); if (first) evfirst[sid] = evprev[sid]; }
           if (P.start_status && !single) P.start_status[tape_off + sid] = sstat[sl];
           if (P.start_iters && !single) P.start_iters[tape_off + sid] = siter[sl];
           if (!bad && (si[I_BEST] < 0 || f < misc[0] || (f == misc[0] && sid < si[I_BEST]))) {
             si[I_BEST] = sid; misc[0] = f;
             for (int a = 0; a < d; ++a) bestx[a] = x[a];
           }
-          if (si[I_NEXT] < P.S) { load_start(sl, si[I_NEXT]); si[I_NEXT] += 1; alist[na2++] = sl; }
+          if (si[I_NEXT] < P.S) { load_start(sl, (int)sorder[si[I_NEXT]]); si[I_NEXT] += 1; alist[na2++] = sl; }
         }
         si[I_NACT] = na2;
       }
@@ -1656,6 +1673,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) RBO_KERNEL_NAME(const __grid_c
   int* si = k.si;
   k.build_tables();
   for (int i = tid; i < 2 * d; i += RBO_THREADS) smem[P.pl.sbnd + i] = i < d ? P.lbs[i] : P.ubs[i - d];
+  for (int i = tid; i < P.S; i += RBO_THREADS) { k.evprev[i] = 0; k.evfirst[i] = 0; }
   k.pipe_init();
   for (int i = tid; i < NR * RP; i += RBO_THREADS) k.V[i] = 0.0;  // rows beyond the fantasy block are read (times exact zeros of L0's padding) but never written
   if (P.xsm) for (int i = tid; i < d * N8; i += RBO_THREADS) k.Xs[(i / N8) * P.XP + (i % N8)] = __ldg(P.Xb + i);
@@ -1709,7 +1727,7 @@ __global__ void __launch_bounds__(RBO_THREADS, 1) RBO_KERNEL_NAME(const __grid_c
             // cs[fantasy_index + 2] (1-based) = the coefficients after `step` fantasies -- or, myopic,
             // multistart_base_solve!(::Surrogate, ...) (rbf_optim.jl:103-134): the base surrogate, no fantasies
             if (single) __syncthreads();
-            k.multistart(single ? 0 : (myopic ? (size_t)m * P.S : ((size_t)m * h + (step - 1)) * P.S), single);
+            k.multistart(single ? 0 : (myopic ? (size_t)m * P.S : ((size_t)m * h + (step - 1)) * P.S), single, !single && step == 1);
           }
           __syncthreads();
           if (!single) {
