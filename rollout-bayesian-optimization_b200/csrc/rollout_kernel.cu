@@ -164,7 +164,8 @@ __device__ __noinline__ void bwd_direct(double* V, const double* Fp, const int* 
         if (v1) V[(size_t)(N8 + g) * RP + c1] = w1;
       }
     }
-    if (scratch) {
+#if RBO_VGLOB
+    {
       // ---- large-n variant: task = (column group, pair of block rows {c, nb-1-c} -- equal work --); a warp takes all four row
       // quarters of its block rows, so every right-hand-side fragment read from the (global, L2-resident) work matrix feeds four
       // tensor-core tiles. The panels stream straight from L2 in A-fragment order. Results go to a per-CTA scratch (out of place:
@@ -221,8 +222,8 @@ __device__ __noinline__ void bwd_direct(double* V, const double* Fp, const int* 
         const int group = idx / (N8 * 8), r2 = idx - group * N8 * 8, row = r2 >> 3, cc = r2 & 7;
         if (8 * group + cc < ncols) V[(size_t)row * RP + colidx[8 * group + cc]] = scratch[idx];
       }
-      return;
     }
+#else  // the shared-memory build never takes the scratch path and the large-n build always does: each compiles only its own
     // ---- base rows: w_I = sum_{J >= I} Linv[J][I]^T b_J ; one task per warp and batch, a batch = whole column groups
     const int gpb = RBO_NWARPS / tpg;  // column groups per batch (tpg <= RBO_NWARPS is the caller's condition)
     for (int gb = 0; gb < ngroups; gb += gpb) {
@@ -242,23 +243,19 @@ __device__ __noinline__ void bwd_direct(double* V, const double* Fp, const int* 
         const double2* ap = reinterpret_cast<const double2*>(Lbf) + (size_t)(chunk0 * 4 + rq) * 128 + lane;  // 128 double2 per tile, 512 per chunk
         const double* vd = V + (rb + tg) * RP + cB;  // right-hand-side rows of block ib (used by the last, diagonal tile)
         double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;  // two accumulator chains over the whole block row
-        double2 A[4], An[4];
+        // the A fragments of the next tile are loaded into the registers of the fragment that has just been issued (no second buffer:
+        // the function has to live with the registers the caller leaves it, and a spilled prefetch buffer is worse than a shorter distance)
+        double2 A[4];
 #pragma unroll
         for (int pp = 0; pp < 4; ++pp) A[pp] = __ldg(ap + 32 * pp);
         for (int cc = 0; cc < nc; ++cc) {
           const double* v = (cc < nc - 1) ? vd + (RBO_BR + RBO_CHUNK_K * cc) * RP : vd;
-          if (cc + 1 < nc) {
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp) An[pp] = __ldg(ap + 512 * (cc + 1) + 32 * pp);
-          }
+          const double2* an = ap + 512 * (cc + 1 < nc ? cc + 1 : cc);
 #pragma unroll
           for (int pp = 0; pp < 4; ++pp) {
             dmma(e0, e1, A[pp].x, v[pp * rp8]);
             dmma(o0, o1, A[pp].y, v[pp * rp8 + rp4]);
-          }
-          if (cc + 1 < nc) {
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp) A[pp] = An[pp];
+            A[pp] = __ldg(an + 32 * pp);
           }
         }
         acc[hh][0] = e0 + o0; acc[hh][1] = e1 + o1;
@@ -277,6 +274,7 @@ __device__ __noinline__ void bwd_direct(double* V, const double* Fp, const int* 
         }
       }
     }
+#endif
   }
 
 
