@@ -36,7 +36,7 @@ import __graft_entry__ as graft  # noqa: E402
 METRIC = "rollout trajectories/sec (value+grad)"
 UNIT = "trajectories/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the rollout kernel (ncu --set full, 1 GPU, default M): (bytes, capture)
-TRAFFIC_NCU = {"C3": (127757824, "profiles/r3_dram_c3_fullM.csv")}  # algorithmic: 15.7 MB (normals + dual directions); the rest is local-memory (stack / spill) lines written back from L2
+TRAFFIC_NCU = {"C3": (120366848, "profiles/r3_dram_c3_fullM.csv")}  # algorithmic: 15.7 MB (normals + dual directions); the rest is local-memory (stack / spill) lines written back from L2
 
 
 def parse():
