@@ -122,7 +122,7 @@ __device__ __forceinline__ void fan_wbot(const double* V, const double* Fp, int 
 
   // V <- L^-T V (N <= 256), every warp of the CTA working: the backward pass of the inner
   // solve has <= 8 columns, far too few to keep a staged panel stream busy, so here the panels of L0^-1 (A-fragment order,
-  // Lbf) are read straight from L2, three tiles in flight per warp. Task = (column group, pair of block rows {c, nb-1-c}
+  // Lbf) are read straight from L2, prefetched one tile ahead in place. Task = (column group, pair of block rows {c, nb-1-c}
   // -- equal work --, row quarter). Results stay in registers until every warp has finished reading the right-hand sides.
 __device__ __noinline__ void bwd_direct(double* V, const double* Fp, const int* colidx, const double* Lbf, int RP, int N8, int nb, int ncols, int nfan, int warp, int lane, double* scratch = nullptr) {
     const unsigned FULL = 0xffffffffu;
