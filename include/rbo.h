@@ -147,7 +147,7 @@ int rbo_get_normals(rbo_handle* h, double* out);
  * nodes / weights to nodes[indices[i]], weights[indices[i]] (rollout.jl:431-432). nodes, weights: depth x m_count,
  * column-major (step fastest), depth >= horizon + 1. Used by rbo_rollout with RBO_FLAG_GAUSS_HERMITE. */
 int rbo_set_quadrature(rbo_handle* h, const double* nodes, const double* weights, int depth, int m_count);
-/* inner_solve_xstarts (rollout.jl:282): d x S, S = number of columns (the reference passes S+2). */
+/* inner_solve_xstarts (rollout.jl:282): d x S, S = number of columns (the reference passes S+2). S <= 65535. */
 int rbo_set_starts(rbo_handle* h, const double* starts, int S);
 
 /* ---- the hot path ---------------------------------------------------------------------------- */

@@ -463,6 +463,7 @@ int rbo_set_starts(rbo_handle* h, const double* starts, int S) {
   if (!h) return RBO_ERR_ARG;
   if (!h->have_sur) return fail(h, RBO_ERR_STATE, "rbo_set_starts: call rbo_set_surrogate first");
   if (!starts || S < 1) return fail(h, RBO_ERR_ARG, "rbo_set_starts: bad arguments");
+  if (S > 65535) return fail(h, RBO_ERR_UNSUPPORTED, "rbo_set_starts: %d starts (the kernel keeps per-start counters and the hand-out order as 16-bit values: at most 65535)", S);
   CK(h, cudaSetDevice(h->device));
   CK(h, dev_reserve(&h->starts, &h->cap_starts, (size_t)S * h->d));
   CK(h, cudaMemcpyAsync(h->starts, starts, (size_t)S * h->d * 8, cudaMemcpyHostToDevice, h->stream));
